@@ -1,0 +1,576 @@
+// rtz_api.cu — host side of librtz.so: the C ABI declared in include/rtz.h.
+// Replaces the body of Camera.render (reference src/camera.zig:123-145) and PPM.saveBinary
+// (src/ppm.zig:42-60).  There is no CPU fallback anywhere in this file: every compute entry
+// point needs a CUDA device and fails with RTZ_ERR_NO_DEVICE / RTZ_ERR_CUDA otherwise.
+#include <cuda_runtime.h>
+
+#include <cerrno>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/rtz.h"
+#include "rtz_kernels.cuh"
+
+namespace {
+
+thread_local std::string g_last_error;
+
+#define RTZ_CUDA(call)                                                                              \
+    do {                                                                                            \
+        cudaError_t e_ = (call);                                                                    \
+        if (e_ != cudaSuccess) {                                                                    \
+            g_last_error = std::string(#call) + ": " + cudaGetErrorString(e_);                      \
+            return (e_ == cudaErrorNoDevice || e_ == cudaErrorInsufficientDriver) ? RTZ_ERR_NO_DEVICE \
+                                                                                  : RTZ_ERR_CUDA;   \
+        }                                                                                           \
+    } while (0)
+
+uint64_t os_seed() {  // Scene.init with seed == null draws from getrandom (src/Scene.zig:33-36)
+    uint64_t s = 0;
+    FILE* f = std::fopen("/dev/urandom", "rb");
+    if (f) {
+        if (std::fread(&s, 1, sizeof(s), f) != sizeof(s)) s = 0x9e3779b97f4a7c15ULL;
+        std::fclose(f);
+    }
+    return s;
+}
+
+inline float bits_to_float(int32_t v) {
+    float f;
+    std::memcpy(&f, &v, 4);
+    return f;
+}
+
+template <class T>
+struct DevBuf {
+    T* p = nullptr;
+    size_t cap = 0;
+    cudaError_t reserve(size_t n) {
+        if (n <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr, cap = 0;
+        cudaError_t e = cudaMalloc(&p, n * sizeof(T));
+        if (e == cudaSuccess) cap = n;
+        return e;
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr, cap = 0;
+    }
+};
+
+}  // namespace
+
+struct rtz_context {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    int sm_count = 0;
+    size_t smem_optin = 0;
+    // scene (device SoA f32 + the f64 copy the legacy kernel reads)
+    DevBuf<float4> geom, aux, albedo;
+    DevBuf<rtz::DSphere> dspheres;
+    int n_spheres = 0, n_pad = 0;
+    // frame state
+    DevBuf<unsigned long long> accum;
+    DevBuf<unsigned long long> counters;  // [0] queue head, [1..4] stats
+    DevBuf<uint8_t> rgb;                  // used by the host-buffer entry points
+    DevBuf<double> linear;
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    unsigned long long* h_counters = nullptr;  // pinned
+};
+
+namespace {
+
+int32_t shard_geom(uint64_t W, uint64_t H, const rtz_shard* s, rtz::ShardGeom& g) {
+    rtz_shard d{0, 1, (uint32_t)W, 1};  // whole frame: tiles are rows -> compact layout == row-major image
+    if (s) d = *s;
+    if (d.world == 0 || d.rank >= d.world || d.tile_w == 0 || d.tile_h == 0) return RTZ_ERR_BAD_ARG;
+    g.rank = d.rank, g.world = d.world, g.tile_w = d.tile_w, g.tile_h = d.tile_h;
+    g.tiles_x = (uint32_t)((W + d.tile_w - 1) / d.tile_w);
+    g.tiles_y = (uint32_t)((H + d.tile_h - 1) / d.tile_h);
+    const uint64_t tiles = (uint64_t)g.tiles_x * g.tiles_y;
+    // every rank gets the size of rank 0 (the largest) so gathered buffers are equal-sized
+    g.n_local_tiles = (uint32_t)((tiles + d.world - 1) / d.world);
+    g.tile_pixels = d.tile_w * d.tile_h;
+    return RTZ_OK;
+}
+
+int32_t check_camera(const rtz_camera* c) {
+    if (!c || c->width == 0 || c->height == 0) return RTZ_ERR_BAD_ARG;
+    if (c->width * c->height > 0xFFFFFFFFull) return RTZ_ERR_BAD_ARG;
+    if (c->mode < RTZ_MODE_PATH || c->mode > RTZ_MODE_LEGACY_NORMAL) return RTZ_ERR_BAD_ARG;
+    if (c->samples_per_pixel == 0 || c->samples_per_pixel > 0x7FFFFFFFull) return RTZ_ERR_BAD_ARG;
+    if (c->mode != RTZ_MODE_PATH && c->samples_per_pixel != 1) return RTZ_ERR_BAD_ARG;
+    if (c->bounce_max > 0xFFFFFFFFull) return RTZ_ERR_BAD_ARG;
+    return RTZ_OK;
+}
+
+rtz::DevCamera to_dev_camera(const rtz_camera& c, uint64_t seed) {
+    rtz::DevCamera d;
+    d.p0x = (float)c.pixel0[0], d.p0y = (float)c.pixel0[1], d.p0z = (float)c.pixel0[2];
+    d.dux = (float)c.du[0], d.duy = (float)c.du[1], d.duz = (float)c.du[2];
+    d.dvx = (float)c.dv[0], d.dvy = (float)c.dv[1], d.dvz = (float)c.dv[2];
+    d.cx = (float)c.center[0], d.cy = (float)c.center[1], d.cz = (float)c.center[2];
+    d.uux = (float)c.defocus_disk_u[0], d.uuy = (float)c.defocus_disk_u[1], d.uuz = (float)c.defocus_disk_u[2];
+    d.vvx = (float)c.defocus_disk_v[0], d.vvy = (float)c.defocus_disk_v[1], d.vvz = (float)c.defocus_disk_v[2];
+    d.tmin = (float)c.t_min;
+    d.defocus = c.defocus_angle > 0 ? 1 : 0;  // src/camera.zig:191
+    d.width = (uint32_t)c.width, d.height = (uint32_t)c.height;
+    d.spp = (uint32_t)c.samples_per_pixel, d.bounce_max = (uint32_t)c.bounce_max;
+    d.key0 = (uint32_t)seed, d.key1 = (uint32_t)(seed >> 32);
+    return d;
+}
+
+// chunk size: <= 256 samples of one pixel, and enough chunks to keep every warp busy
+uint32_t pick_chunk(uint32_t spp) { return spp < 256u ? spp : 256u; }
+
+template <int kBlock>
+int32_t launch_trace(rtz_context* ctx, const rtz::TraceParams& P, size_t smem) {
+    auto kern = rtz::trace_kernel<kBlock>;
+    RTZ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 0;
+    RTZ_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kBlock, smem));
+    if (per_sm < 1) {
+        g_last_error = "scene does not fit in shared memory";
+        return RTZ_ERR_TOO_MANY_SPHERES;
+    }
+    const uint64_t warps_wanted = (P.n_chunks + 0) ;
+    uint64_t blocks = (uint64_t)ctx->sm_count * per_sm;
+    const uint64_t max_useful = (warps_wanted + (kBlock / 32) - 1) / (kBlock / 32);
+    if (blocks > max_useful) blocks = max_useful ? max_useful : 1;
+    kern<<<(unsigned)blocks, kBlock, smem, ctx->stream>>>(P);
+    RTZ_CUDA(cudaGetLastError());
+    return RTZ_OK;
+}
+
+int32_t render_path(rtz_context* ctx, const rtz_camera* cam, const rtz::ShardGeom& sg, uint8_t* d_rgb,
+                    double* d_linear, rtz_stats* st, uint64_t seed) {
+    if (ctx->n_spheres <= 0) return RTZ_ERR_BAD_ARG;
+    const uint64_t n_local_pixels = (uint64_t)sg.n_local_tiles * sg.tile_pixels;
+    if (n_local_pixels > 0xFFFFFFFFull) return RTZ_ERR_BAD_ARG;
+    RTZ_CUDA(ctx->accum.reserve(3 * n_local_pixels));
+    rtz::TraceParams P;
+    P.cam = to_dev_camera(*cam, seed);
+    P.sh = sg;
+    P.geom = ctx->geom.p, P.aux = ctx->aux.p, P.albedo = ctx->albedo.p;
+    P.n_spheres = ctx->n_spheres, P.n_pad = ctx->n_pad;
+    P.chunk = pick_chunk(P.cam.spp);
+    P.chunks_per_pixel = (P.cam.spp + P.chunk - 1) / P.chunk;
+    P.n_chunks = n_local_pixels * P.chunks_per_pixel;
+    P.accum = ctx->accum.p;
+    P.counter = ctx->counters.p;
+    P.stats = ctx->counters.p + 1;
+    const size_t smem = (size_t)ctx->n_pad * 48;
+    if (smem + 1024 > ctx->smem_optin) {
+        g_last_error = "scene does not fit in shared memory";
+        return RTZ_ERR_TOO_MANY_SPHERES;
+    }
+    RTZ_CUDA(cudaEventRecord(ctx->ev[0], ctx->stream));
+    RTZ_CUDA(cudaMemsetAsync(ctx->accum.p, 0, 3 * n_local_pixels * sizeof(unsigned long long), ctx->stream));
+    RTZ_CUDA(cudaMemsetAsync(ctx->counters.p, 0, 8 * sizeof(unsigned long long), ctx->stream));
+    RTZ_CUDA(cudaEventRecord(ctx->ev[1], ctx->stream));
+    int32_t rc = (smem > 96 * 1024) ? launch_trace<512>(ctx, P, smem) : launch_trace<256>(ctx, P, smem);
+    if (rc != RTZ_OK) return rc;
+    RTZ_CUDA(cudaEventRecord(ctx->ev[2], ctx->stream));
+    const uint64_t n3 = 3 * n_local_pixels;
+    rtz::resolve_kernel<<<(unsigned)((n3 + 255) / 256), 256, 0, ctx->stream>>>(
+        ctx->accum.p, n_local_pixels, cam->pixel_samples_scale, d_rgb, d_linear);
+    RTZ_CUDA(cudaGetLastError());
+    RTZ_CUDA(cudaEventRecord(ctx->ev[3], ctx->stream));
+    RTZ_CUDA(cudaMemcpyAsync(ctx->h_counters, ctx->counters.p, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost,
+                             ctx->stream));
+    RTZ_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (st) {
+        std::memset(st, 0, sizeof(*st));
+        st->samples = ctx->h_counters[1], st->segments = ctx->h_counters[2];
+        st->depth_capped = ctx->h_counters[3], st->absorbed = ctx->h_counters[4];
+        st->sphere_tests = st->segments * (uint64_t)ctx->n_spheres;
+        st->kernel_launches = 2;
+        float ms = 0;
+        cudaEventElapsedTime(&ms, ctx->ev[1], ctx->ev[2]), st->trace_ms = ms;
+        cudaEventElapsedTime(&ms, ctx->ev[2], ctx->ev[3]), st->resolve_ms = ms;
+        cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[3]), st->total_ms = ms;
+        st->seed_used = seed;
+    }
+    return RTZ_OK;
+}
+
+int32_t render_legacy(rtz_context* ctx, const rtz_camera* cam, uint8_t* d_rgb, double* d_linear, rtz_stats* st) {
+    rtz::LegacyParams P;
+    for (int k = 0; k < 3; ++k) P.p0[k] = cam->pixel0[k], P.du[k] = cam->du[k], P.dv[k] = cam->dv[k], P.c[k] = cam->center[k];
+    P.tmin = cam->t_min, P.tmax = cam->t_max;
+    P.width = (uint32_t)cam->width, P.height = (uint32_t)cam->height;
+    P.mode = cam->mode, P.n = ctx->n_spheres, P.spheres = ctx->dspheres.p;
+    const uint32_t n = P.width * P.height;
+    RTZ_CUDA(cudaEventRecord(ctx->ev[0], ctx->stream));
+    rtz::legacy_kernel<<<(n + 127) / 128, 128, 0, ctx->stream>>>(P, d_rgb, d_linear);
+    RTZ_CUDA(cudaGetLastError());
+    RTZ_CUDA(cudaEventRecord(ctx->ev[3], ctx->stream));
+    RTZ_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (st) {
+        std::memset(st, 0, sizeof(*st));
+        st->samples = n;
+        st->segments = cam->mode == RTZ_MODE_LEGACY_SKY ? 0 : n;
+        st->sphere_tests = st->segments * (uint64_t)ctx->n_spheres;
+        st->kernel_launches = 1;
+        float ms = 0;
+        cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[3]), st->trace_ms = st->total_ms = ms;
+    }
+    return RTZ_OK;
+}
+
+struct ScopedCtx {  // context for the one-shot entry points
+    rtz_context* c = nullptr;
+    ~ScopedCtx() {
+        if (c) rtz_context_destroy(c);
+    }
+};
+
+}  // namespace
+
+// =================================================================================================
+extern "C" {
+
+int32_t rtz_abi_version(void) { return RTZ_ABI_VERSION; }
+
+const char* rtz_strerror(int32_t s) {
+    switch (s) {
+        case RTZ_OK: return "ok";
+        case RTZ_ERR_BAD_ARG: return "bad argument";
+        case RTZ_ERR_NO_DEVICE: return "no CUDA device (librtz has no CPU fallback)";
+        case RTZ_ERR_CUDA: return "CUDA error";
+        case RTZ_ERR_IO: return "I/O error";
+        case RTZ_ERR_TOO_MANY_SPHERES: return "scene does not fit in shared memory";
+        case RTZ_ERR_ARCH: return "device is not sm_100 (librtz ships sm_100a code only)";
+        default: return "unknown status";
+    }
+}
+const char* rtz_last_error(void) { return g_last_error.c_str(); }
+
+int32_t rtz_device_count(int32_t* count_out) {
+    if (!count_out) return RTZ_ERR_BAD_ARG;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) {
+        g_last_error = cudaGetErrorString(e);
+        *count_out = 0;
+        return RTZ_ERR_NO_DEVICE;
+    }
+    *count_out = n;
+    return n > 0 ? RTZ_OK : RTZ_ERR_NO_DEVICE;
+}
+
+int32_t rtz_context_create(int32_t device, void* stream, rtz_context** out) {
+    if (!out) return RTZ_ERR_BAD_ARG;
+    *out = nullptr;
+    int n = 0;
+    int32_t rc = rtz_device_count(&n);
+    if (rc != RTZ_OK) return rc;
+    if (device < 0) RTZ_CUDA(cudaGetDevice(&device));
+    if (device >= n) return RTZ_ERR_BAD_ARG;
+    RTZ_CUDA(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    RTZ_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10) {
+        g_last_error = std::string("device ") + prop.name + " is sm_" + std::to_string(prop.major * 10 + prop.minor);
+        return RTZ_ERR_ARCH;
+    }
+    rtz_context* c = new rtz_context();
+    c->device = device;
+    c->sm_count = prop.multiProcessorCount;
+    c->smem_optin = prop.sharedMemPerBlockOptin;
+    if (stream) {
+        c->stream = (cudaStream_t)stream;
+    } else {
+        cudaError_t e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
+        if (e != cudaSuccess) {
+            delete c;
+            g_last_error = cudaGetErrorString(e);
+            return RTZ_ERR_CUDA;
+        }
+        c->own_stream = true;
+    }
+    for (auto& e : c->ev) cudaEventCreate(&e);
+    cudaMallocHost(&c->h_counters, 8 * sizeof(unsigned long long));
+    if (c->counters.reserve(8) != cudaSuccess || !c->h_counters) {
+        rtz_context_destroy(c);
+        g_last_error = "allocation failed";
+        return RTZ_ERR_CUDA;
+    }
+    *out = c;
+    return RTZ_OK;
+}
+
+int32_t rtz_context_destroy(rtz_context* c) {
+    if (!c) return RTZ_ERR_BAD_ARG;
+    cudaSetDevice(c->device);
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    c->geom.release(), c->aux.release(), c->albedo.release(), c->dspheres.release();
+    c->accum.release(), c->counters.release(), c->rgb.release(), c->linear.release();
+    for (auto& e : c->ev)
+        if (e) cudaEventDestroy(e);
+    if (c->h_counters) cudaFreeHost(c->h_counters);
+    if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+    return RTZ_OK;
+}
+
+int32_t rtz_scene_upload(rtz_context* c, const rtz_sphere* sp, uint64_t n) {
+    if (!c || (!sp && n) || n > (1u << 20)) return RTZ_ERR_BAD_ARG;
+    RTZ_CUDA(cudaSetDevice(c->device));
+    const int n_pad = (int)((n + 3) & ~3ull);
+    std::vector<float4> g(n_pad), a(n_pad), al(n_pad);
+    std::vector<rtz::DSphere> ds(n ? n : 1);
+    for (uint64_t i = 0; i < n; ++i) {
+        const rtz_sphere& s = sp[i];
+        if (s.mat_type < RTZ_MAT_LAMBERTIAN || s.mat_type > RTZ_MAT_DIELECTRIC) return RTZ_ERR_BAD_ARG;
+        const float r = (float)(s.radius < 0 ? 0.0 : s.radius);  // Sphere.init clamp (src/sphere.zig:21)
+        g[i] = make_float4((float)s.center[0], (float)s.center[1], (float)s.center[2], r * r);
+        const float param = s.mat_type == RTZ_MAT_METAL ? (float)s.fuzz : (float)s.refraction_index;
+        a[i] = make_float4(r, 1.0f / r, param, bits_to_float(s.mat_type));
+        al[i] = make_float4((float)s.albedo[0], (float)s.albedo[1], (float)s.albedo[2],
+                            1.0f / (float)s.refraction_index);
+        ds[i] = rtz::DSphere{s.center[0], s.center[1], s.center[2], s.radius < 0 ? 0.0 : s.radius};
+    }
+    for (int i = (int)n; i < n_pad; ++i) {  // padding: r^2 = -inf makes the discriminant -inf
+        g[i] = make_float4(0.f, 0.f, 0.f, -INFINITY);
+        a[i] = make_float4(0.f, 0.f, 0.f, bits_to_float(0));
+        al[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    if (n_pad) {
+        RTZ_CUDA(c->geom.reserve(n_pad));
+        RTZ_CUDA(c->aux.reserve(n_pad));
+        RTZ_CUDA(c->albedo.reserve(n_pad));
+        RTZ_CUDA(cudaMemcpyAsync(c->geom.p, g.data(), n_pad * sizeof(float4), cudaMemcpyHostToDevice, c->stream));
+        RTZ_CUDA(cudaMemcpyAsync(c->aux.p, a.data(), n_pad * sizeof(float4), cudaMemcpyHostToDevice, c->stream));
+        RTZ_CUDA(cudaMemcpyAsync(c->albedo.p, al.data(), n_pad * sizeof(float4), cudaMemcpyHostToDevice, c->stream));
+    }
+    RTZ_CUDA(c->dspheres.reserve(ds.size()));
+    RTZ_CUDA(cudaMemcpyAsync(c->dspheres.p, ds.data(), ds.size() * sizeof(rtz::DSphere), cudaMemcpyHostToDevice,
+                             c->stream));
+    RTZ_CUDA(cudaStreamSynchronize(c->stream));  // the staging vectors die here
+    c->n_spheres = (int)n, c->n_pad = n_pad;
+    return RTZ_OK;
+}
+
+uint64_t rtz_shard_pixels(uint64_t W, uint64_t H, const rtz_shard* s) {
+    rtz::ShardGeom g;
+    if (shard_geom(W, H, s, g) != RTZ_OK) return 0;
+    return (uint64_t)g.n_local_tiles * g.tile_pixels;
+}
+
+static int32_t render_resident_impl(rtz_context* c, const rtz_camera* cam, const rtz_shard* shard, uint8_t* d_rgb,
+                                    double* d_linear, rtz_stats* st) {
+    if (!c || !d_rgb) return RTZ_ERR_BAD_ARG;
+    int32_t rc = check_camera(cam);
+    if (rc != RTZ_OK) return rc;
+    RTZ_CUDA(cudaSetDevice(c->device));
+    if (cam->mode != RTZ_MODE_PATH) {
+        if (shard && shard->world != 1) return RTZ_ERR_BAD_ARG;  // the legacy modes are whole-frame only
+        return render_legacy(c, cam, d_rgb, d_linear, st);
+    }
+    rtz::ShardGeom g;
+    rc = shard_geom(cam->width, cam->height, shard, g);
+    if (rc != RTZ_OK) return rc;
+    const uint64_t seed = cam->has_seed ? cam->seed : os_seed();
+    return render_path(c, cam, g, d_rgb, d_linear, st, seed);
+}
+
+int32_t rtz_render_resident(rtz_context* c, const rtz_camera* cam, const rtz_shard* shard, uint8_t* d_rgb,
+                            rtz_stats* st) {
+    return render_resident_impl(c, cam, shard, d_rgb, nullptr, st);
+}
+
+int32_t rtz_deinterleave(rtz_context* c, uint64_t W, uint64_t H, uint32_t world, uint32_t tw, uint32_t th,
+                         const uint8_t* d_gathered, uint8_t* d_rgb) {
+    if (!c || !d_gathered || !d_rgb || !W || !H) return RTZ_ERR_BAD_ARG;
+    rtz_shard s{0, world, tw, th};
+    rtz::ShardGeom g;
+    int32_t rc = shard_geom(W, H, &s, g);
+    if (rc != RTZ_OK) return rc;
+    RTZ_CUDA(cudaSetDevice(c->device));
+    const uint64_t n = W * H;
+    rtz::deinterleave_kernel<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(
+        d_gathered, (uint64_t)g.n_local_tiles * g.tile_pixels, (uint32_t)W, (uint32_t)H, world, tw, th, g.tiles_x, d_rgb);
+    RTZ_CUDA(cudaGetLastError());
+    RTZ_CUDA(cudaStreamSynchronize(c->stream));
+    return RTZ_OK;
+}
+
+int32_t rtz_render_linear(const rtz_camera* cam, const rtz_sphere* sp, uint64_t n, uint8_t* rgb_out,
+                          double* linear_out, rtz_stats* st) {
+    if (!rgb_out || (!sp && n)) return RTZ_ERR_BAD_ARG;
+    int32_t rc = check_camera(cam);
+    if (rc != RTZ_OK) return rc;
+    ScopedCtx sc;
+    rc = rtz_context_create(-1, nullptr, &sc.c);
+    if (rc != RTZ_OK) return rc;
+    rtz_context* c = sc.c;
+    rc = rtz_scene_upload(c, sp, n);
+    if (rc != RTZ_OK) return rc;
+    const uint64_t px = cam->width * cam->height;
+    RTZ_CUDA(c->rgb.reserve(3 * px));
+    if (linear_out) RTZ_CUDA(c->linear.reserve(3 * px));
+    rc = render_resident_impl(c, cam, nullptr, c->rgb.p, linear_out ? c->linear.p : nullptr, st);
+    if (rc != RTZ_OK) return rc;
+    RTZ_CUDA(cudaMemcpyAsync(rgb_out, c->rgb.p, 3 * px, cudaMemcpyDeviceToHost, c->stream));
+    if (linear_out)
+        RTZ_CUDA(cudaMemcpyAsync(linear_out, c->linear.p, 3 * px * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    RTZ_CUDA(cudaStreamSynchronize(c->stream));
+    return RTZ_OK;
+}
+
+int32_t rtz_render(const rtz_camera* cam, const rtz_sphere* sp, uint64_t n, uint8_t* rgb_out, rtz_stats* st) {
+    return rtz_render_linear(cam, sp, n, rgb_out, nullptr, st);
+}
+
+int32_t rtz_write_ppm(const char* path, uint64_t w, uint64_t h, const uint8_t* rgb) {
+    if (!path || (!rgb && w * h)) return RTZ_ERR_BAD_ARG;
+    FILE* f = std::fopen(path, "wb");
+    if (!f) {
+        g_last_error = std::string(path) + ": " + std::strerror(errno);
+        return RTZ_ERR_IO;
+    }
+    bool ok = std::fprintf(f, "P6\n%llu %llu\n255\n", (unsigned long long)w, (unsigned long long)h) > 0;
+    const size_t nb = (size_t)(3 * w * h);
+    ok = ok && std::fwrite(rgb, 1, nb, f) == nb;
+    ok = ok && std::fputc('\n', f) != EOF;  // trailing newline (src/ppm.zig:57)
+    ok = (std::fclose(f) == 0) && ok;
+    return ok ? RTZ_OK : RTZ_ERR_IO;
+}
+
+// ---- probes -------------------------------------------------------------------------------------
+int32_t rtz_probe_hit(const rtz_sphere* sp, uint64_t n, const double o[3], const double d[3], double tmin, double tmax,
+                      rtz_hit* out) {
+    if (!sp || !n || !o || !d || !out) return RTZ_ERR_BAD_ARG;
+    ScopedCtx sc;
+    int32_t rc = rtz_context_create(-1, nullptr, &sc.c);
+    if (rc != RTZ_OK) return rc;
+    rc = rtz_scene_upload(sc.c, sp, n);
+    if (rc != RTZ_OK) return rc;
+    rtz::ProbeHitOut* dout;
+    RTZ_CUDA(cudaMalloc(&dout, sizeof(*dout)));
+    rtz::probe_hit_kernel<<<1, 1, 0, sc.c->stream>>>(sc.c->geom.p, sc.c->aux.p, sc.c->n_pad, (float)o[0], (float)o[1],
+                                                    (float)o[2], (float)d[0], (float)d[1], (float)d[2], (float)tmin,
+                                                    (float)tmax, dout);
+    rtz::ProbeHitOut h;
+    cudaError_t e = cudaMemcpyAsync(&h, dout, sizeof(h), cudaMemcpyDeviceToHost, sc.c->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(sc.c->stream);
+    cudaFree(dout);
+    RTZ_CUDA(e);
+    std::memset(out, 0, sizeof(*out));
+    out->hit = h.hit;
+    if (h.hit) {
+        out->index = h.index, out->front = h.front;
+        out->t = (double)h.t / (double)h.len;  // back to the reference's units of |dir|
+        for (int k = 0; k < 3; ++k) out->point[k] = h.p[k], out->normal[k] = h.n[k];
+    }
+    return RTZ_OK;
+}
+
+int32_t rtz_probe_scatter(const rtz_sphere* sp, uint64_t n, int32_t index, const double o[3], const double d[3],
+                          uint64_t seed, uint32_t pixel, uint32_t sample, uint32_t bounce, rtz_scatter* out) {
+    if (!sp || !n || index < 0 || (uint64_t)index >= n || !o || !d || !out) return RTZ_ERR_BAD_ARG;
+    ScopedCtx sc;
+    int32_t rc = rtz_context_create(-1, nullptr, &sc.c);
+    if (rc != RTZ_OK) return rc;
+    rc = rtz_scene_upload(sc.c, sp, n);
+    if (rc != RTZ_OK) return rc;
+    rtz_camera cam;
+    std::memset(&cam, 0, sizeof(cam));
+    cam.t_min = 1e-3, cam.bounce_max = 0xFFFFFFFFull, cam.samples_per_pixel = 1, cam.width = cam.height = 1;
+    const rtz::DevCamera dc = to_dev_camera(cam, seed);
+    rtz::ProbeScatterOut* dout;
+    RTZ_CUDA(cudaMalloc(&dout, sizeof(*dout)));
+    rtz::probe_scatter_kernel<<<1, 1, 0, sc.c->stream>>>(dc, sc.c->geom.p, sc.c->aux.p, sc.c->albedo.p, index,
+                                                        (float)o[0], (float)o[1], (float)o[2], (float)d[0], (float)d[1],
+                                                        (float)d[2], pixel, sample, bounce, dout);
+    rtz::ProbeScatterOut h;
+    cudaError_t e = cudaMemcpyAsync(&h, dout, sizeof(h), cudaMemcpyDeviceToHost, sc.c->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(sc.c->stream);
+    cudaFree(dout);
+    RTZ_CUDA(e);
+    std::memset(out, 0, sizeof(*out));
+    out->scattered = h.scattered;
+    if (h.scattered)
+        for (int k = 0; k < 3; ++k) {
+            out->origin[k] = h.o[k];
+            out->direction[k] = (double)h.d[k] * (double)h.len;
+            out->attenuation[k] = h.att[k];
+        }
+    return RTZ_OK;
+}
+
+int32_t rtz_probe_to_rgb(const double* lin, uint64_t n, uint8_t* rgb_out) {
+    if (!lin || !rgb_out || !n) return RTZ_ERR_BAD_ARG;
+    ScopedCtx sc;
+    int32_t rc = rtz_context_create(-1, nullptr, &sc.c);
+    if (rc != RTZ_OK) return rc;
+    double* dl;
+    uint8_t* dr;
+    RTZ_CUDA(cudaMalloc(&dl, 3 * n * sizeof(double)));
+    cudaError_t e = cudaMalloc(&dr, 3 * n);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(dl, lin, 3 * n * sizeof(double), cudaMemcpyHostToDevice, sc.c->stream);
+    if (e == cudaSuccess) {
+        rtz::probe_to_rgb_kernel<<<(unsigned)((3 * n + 255) / 256), 256, 0, sc.c->stream>>>(dl, 3 * n, dr);
+        e = cudaMemcpyAsync(rgb_out, dr, 3 * n, cudaMemcpyDeviceToHost, sc.c->stream);
+    }
+    if (e == cudaSuccess) e = cudaStreamSynchronize(sc.c->stream);
+    cudaFree(dl), cudaFree(dr);
+    RTZ_CUDA(e);
+    return RTZ_OK;
+}
+
+int32_t rtz_probe_uniform(uint64_t seed, uint32_t pixel, uint32_t sample, uint32_t bounce, uint64_t n, float* out) {
+    if (!out || !n) return RTZ_ERR_BAD_ARG;
+    ScopedCtx sc;
+    int32_t rc = rtz_context_create(-1, nullptr, &sc.c);
+    if (rc != RTZ_OK) return rc;
+    float* dout;
+    RTZ_CUDA(cudaMalloc(&dout, n * sizeof(float)));
+    const uint64_t blocks = (n + 3) / 4;
+    rtz::probe_uniform_kernel<<<(unsigned)((blocks + 127) / 128), 128, 0, sc.c->stream>>>(
+        (uint32_t)seed, (uint32_t)(seed >> 32), pixel, sample, bounce, n, dout);
+    cudaError_t e = cudaMemcpyAsync(out, dout, n * sizeof(float), cudaMemcpyDeviceToHost, sc.c->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(sc.c->stream);
+    cudaFree(dout);
+    RTZ_CUDA(e);
+    return RTZ_OK;
+}
+
+int32_t rtz_measure_fp32_peak(int32_t device, int32_t variant, double* tflops_out) {
+    if (!tflops_out || variant < 0 || variant > 1) return RTZ_ERR_BAD_ARG;
+    ScopedCtx sc;
+    int32_t rc = rtz_context_create(device, nullptr, &sc.c);
+    if (rc != RTZ_OK) return rc;
+    rtz_context* c = sc.c;
+    float* sink;
+    RTZ_CUDA(cudaMalloc(&sink, 4));
+    const int iters = 1 << 14, blocks = c->sm_count * 8, threads = 256;
+    float best_ms = 1e30f;
+    cudaError_t e = cudaSuccess;
+    for (int rep = 0; rep < 6 && e == cudaSuccess; ++rep) {
+        cudaEventRecord(c->ev[0], c->stream);
+        if (variant == 0)
+            rtz::ffma_peak_kernel<0><<<blocks, threads, 0, c->stream>>>(1.0000001f, 1e-7f, iters, sink);
+        else
+            rtz::ffma_peak_kernel<1><<<blocks, threads, 0, c->stream>>>(1.0000001f, 1e-7f, iters, sink);
+        cudaEventRecord(c->ev[1], c->stream);
+        e = cudaStreamSynchronize(c->stream);
+        float ms = 0;
+        cudaEventElapsedTime(&ms, c->ev[0], c->ev[1]);
+        if (rep > 0 && ms < best_ms) best_ms = ms;
+    }
+    cudaFree(sink);
+    RTZ_CUDA(e);
+    const double flops = 2.0 * 16 * (double)iters * (double)blocks * threads;
+    *tflops_out = flops / (best_ms * 1e-3) / 1e12;
+    return RTZ_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,276 @@
+// rtz_device.cuh — device functions of the B200 path tracer (sm_100a).
+//
+// These are the GPU restatements of the reference's per-sample functions:
+//   getRay / sampleSquare / defocusDiskSample   reference src/camera.zig:187-215
+//   HittableList.hit + Sphere.hit                reference src/hittable.zig:64-77, src/sphere.zig:26-54
+//   Lambertian / Metal / Dielectric .scatter     reference src/material.zig:27-110
+//   Vec.reflect / refract / nearZero             reference src/vec.zig:26-29,103-112
+//
+// ARITHMETIC CONTRACT.  Everything is FP32 with IEEE round-to-nearest +, -, *,
+// /, sqrt and EXPLICIT fmaf(); the translation unit is compiled with -fmad=false so the
+// compiler never contracts on its own.  No approximate intrinsics.  The CPU oracle keeps an
+// independent mirror of this contract (oracle/rtz_mirror.cpp) and the parity tests require the
+// two to agree BIT FOR BIT on the fixed-point pixel sums.
+//
+// Differences from the reference's formulation, all distribution-preserving:
+//   * the ray direction is normalised once per segment (a = |d|^2 = 1 in Sphere.hit); t_min is
+//     rescaled by |d| so the (t_min, inf) interval keeps its reference meaning (Q7/Q8);
+//   * |d|^2 and r^2 are hoisted out of the sphere sweep (17 FLOP / test);
+//   * the sphere the ray starts on ("self") is intersected with c = |oc|^2 - r^2 := 0, the exact
+//     value, instead of the FP32-rounded one: this removes the self-intersection bias of a
+//     naive FP32 port (SURVEY §7 risk 5) without touching any other sphere;
+//   * RNG is Philox4x32-10 keyed (seed) with counter (pixel, sample, bounce, block) instead of
+//     one shared sequential Xoshiro stream (north_star); unit vectors come from Marsaglia's
+//     disk method (2 uniforms / attempt, accept pi/4) instead of cube rejection (accept pi/6):
+//     same uniform distribution on the sphere, fewer divergent retries.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace rtz {
+
+// Material type tags live in the .w lane of the aux float4 as integer bits.
+constexpr int kLambertian = 0, kMetal = 1, kDielectric = 2;
+
+struct DevCamera {
+    float p0x, p0y, p0z;     // pixel0
+    float dux, duy, duz;     // du
+    float dvx, dvy, dvz;     // dv
+    float cx, cy, cz;        // center
+    float uux, uuy, uuz;     // defocusDiskU
+    float vvx, vvy, vvz;     // defocusDiskV
+    float tmin;              // Scene.interval.min
+    int defocus;             // defocusAngle > 0
+    uint32_t width, height, spp, bounce_max;
+    uint32_t key0, key1;     // Philox key = seed
+};
+
+// ---------------------------------------------------------------------------------------------
+// Philox4x32-10 (Salmon et al. SC'11).  10 rounds, 2 x (IMAD.HI + IMAD.LO) each.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
+                                               uint32_t k0, uint32_t k1) {
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+        const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+        const uint32_t n0 = hi1 ^ c1 ^ k0, n2 = hi0 ^ c3 ^ k1;
+        c0 = n0, c1 = lo1, c2 = n2, c3 = lo0;
+        k0 += 0x9E3779B9u, k1 += 0xBB67AE85u;
+    }
+    return make_uint4(c0, c1, c2, c3);
+}
+
+// uniform in [0,1): top 24 bits, exact in FP32
+__device__ __forceinline__ float u01(uint32_t x) { return (float)(x >> 8) * 0x1p-24f; }
+// uniform in [-1,1)
+__device__ __forceinline__ float u11(uint32_t x) { return fmaf(2.0f, u01(x), -1.0f); }
+
+struct RngKey {
+    uint32_t k0, k1, pixel, sample;
+};
+
+// Point of the unit disk by rejection, two attempts per Philox block (blocks blk0, blk0+1, ...).
+__device__ __forceinline__ void sample_disk(const RngKey& k, uint32_t bounce, uint4 first, bool use_zw_of_first,
+                                            float& a, float& b, float& s) {
+    // `first` is block 0 of the stream; when use_zw_of_first only its .z/.w are free (the camera
+    // used .x/.y for the pixel jitter).
+    uint4 r = first;
+    uint32_t blk = 0;
+    if (!use_zw_of_first) {
+        a = u11(r.x), b = u11(r.y), s = fmaf(b, b, a * a);
+        if (s < 1.0f) return;
+    }
+    for (;;) {
+        a = u11(r.z), b = u11(r.w), s = fmaf(b, b, a * a);
+        if (s < 1.0f) return;
+        r = philox4x32_10(k.pixel, k.sample, bounce, ++blk, k.k0, k.k1);
+        a = u11(r.x), b = u11(r.y), s = fmaf(b, b, a * a);
+        if (s < 1.0f) return;
+    }
+}
+
+// Vec.randomUnitVec (src/vec.zig:71-80): uniform on the unit sphere.  Marsaglia (1972):
+// (a,b) uniform in the disk, s = a^2+b^2  ->  (2a sqrt(1-s), 2b sqrt(1-s), 1-2s).
+__device__ __forceinline__ void random_unit_vec(const RngKey& k, uint32_t bounce, uint4 block0, float& ux,
+                                                float& uy, float& uz) {
+    float a, b, s;
+    sample_disk(k, bounce, block0, false, a, b, s);
+    const float q = 2.0f * sqrtf(1.0f - s);
+    ux = a * q, uy = b * q, uz = fmaf(-2.0f, s, 1.0f);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Per-lane path state
+// ---------------------------------------------------------------------------------------------
+struct Path {
+    float ox, oy, oz;   // ray origin
+    float dx, dy, dz;   // ray direction, UNIT length
+    float tr, tg, tb;   // throughput (returnColor of rayColor)
+    float tmin_d;       // t_min * |d_unnormalised|
+    int self;           // sphere the origin lies on, -1 for camera rays
+    uint32_t bounce;    // scatters so far
+};
+
+// Store an un-normalised direction: normalise, rescale t_min (Q7/Q8).
+__device__ __forceinline__ void set_direction(Path& p, float dx, float dy, float dz, float tmin) {
+    const float len2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+    const float len = sqrtf(len2);
+    const float inv = 1.0f / len;
+    p.dx = dx * inv, p.dy = dy * inv, p.dz = dz * inv;
+    p.tmin_d = tmin * len;
+}
+
+// Camera.getRay (src/camera.zig:187-200) for pixel (i,j), sample k.sample.
+__device__ __forceinline__ void camera_ray(const DevCamera& c, const RngKey& k, uint32_t i, uint32_t j, Path& p) {
+    const uint4 r = philox4x32_10(k.pixel, k.sample, 0u, 0u, k.k0, k.k1);
+    const float sx = (float)i + (u01(r.x) - 0.5f);  // sampleSquare (:203-209)
+    const float sy = (float)j + (u01(r.y) - 0.5f);
+    const float psx = fmaf(c.dvx, sy, fmaf(c.dux, sx, c.p0x));
+    const float psy = fmaf(c.dvy, sy, fmaf(c.duy, sx, c.p0y));
+    const float psz = fmaf(c.dvz, sy, fmaf(c.duz, sx, c.p0z));
+    p.ox = c.cx, p.oy = c.cy, p.oz = c.cz;
+    if (c.defocus) {  // defocusDiskSample (:212-215)
+        float a, b, s;
+        sample_disk(k, 0u, r, true, a, b, s);
+        p.ox = fmaf(c.vvx, b, fmaf(c.uux, a, c.cx));
+        p.oy = fmaf(c.vvy, b, fmaf(c.uuy, a, c.cy));
+        p.oz = fmaf(c.vvz, b, fmaf(c.uuz, a, c.cz));
+    }
+    set_direction(p, psx - p.ox, psy - p.oy, psz - p.oz, c.tmin);
+    p.tr = p.tg = p.tb = 1.0f;
+    p.self = -1;
+    p.bounce = 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// HittableList.hit: brute-force closest hit over all spheres (src/hittable.zig:64-77), with
+// Sphere.hit's half-b quadratic (src/sphere.zig:26-43) for a unit direction.
+//   geom[i] = {cx, cy, cz, r^2}
+// Fast path per test: 3 FADD + 1 FMUL + 6 FFMA (17 FLOP) + 1 FSETP.  The root is only
+// evaluated when the discriminant is non-negative.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void slow_path(float h, float disc, int i, int self, float tmin_d, float& closest,
+                                          int& best) {
+    if (i == self) disc = h * h;  // exact c = 0 for the sphere we stand on
+    const float sq = sqrtf(disc);
+    float t = h - sq;  // (h - sqrtd)/a with a = 1
+    if (!(t > tmin_d && t < closest)) {  // Interval.surrounds is strict (src/interval.zig:36-38)
+        t = h + sq;
+        if (!(t > tmin_d && t < closest)) return;
+    }
+    closest = t;  // shrinking t_max; ties keep the earlier sphere
+    best = i;
+}
+
+__device__ __forceinline__ void sweep(const float4* __restrict__ geom, int n, const Path& p, float& t_out,
+                                      int& best_out) {
+    float closest = __int_as_float(0x7f800000);  // +inf
+    int best = -1;
+    const float ox = p.ox, oy = p.oy, oz = p.oz, dx = p.dx, dy = p.dy, dz = p.dz;
+#pragma unroll 4
+    for (int i = 0; i < n; ++i) {
+        const float4 s = geom[i];
+        const float ocx = s.x - ox, ocy = s.y - oy, ocz = s.z - oz;
+        const float h = fmaf(dz, ocz, fmaf(dy, ocy, dx * ocx));
+        const float c = fmaf(ocz, ocz, fmaf(ocy, ocy, fmaf(ocx, ocx, -s.w)));
+        const float disc = fmaf(h, h, -c);
+        if (disc >= 0.0f) slow_path(h, disc, i, p.self, p.tmin_d, closest, best);
+    }
+    t_out = closest;
+    best_out = best;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Shading of one finished segment.  Returns true when the sample is finished; then (sr,sg,sb)
+// is its colour.  `term` reports why: 0 sky, 1 absorbed, 2 depth cap.
+//   aux[i]    = {r, 1/r, fuzz | ior, type bits}
+//   albedo[i] = {r, g, b, 1/ior}
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ bool shade(const DevCamera& cam, const RngKey& k, const float4* __restrict__ geom,
+                                      const float4* __restrict__ aux, const float4* __restrict__ albedo, Path& p,
+                                      float t, int best, float& sr, float& sg, float& sb, int& term) {
+    if (best < 0) {
+        // sky (src/camera.zig:171-177): a = 0.5*(unit(dir).y + 1); white*(1-a) + blue*a
+        const float a = 0.5f * (p.dy + 1.0f);
+        const float w = 1.0f - a;
+        sr = p.tr * fmaf(a, 0.5f, w);
+        sg = p.tg * fmaf(a, 0.7f, w);
+        sb = p.tb * fmaf(a, 1.0f, w);
+        term = 0;
+        return true;
+    }
+    const float4 g = geom[best];
+    const float4 ax = aux[best];
+    const float4 al = albedo[best];
+    // HitRecord (src/sphere.zig:44-53)
+    const float px = fmaf(t, p.dx, p.ox), py = fmaf(t, p.dy, p.oy), pz = fmaf(t, p.dz, p.oz);
+    float nx = (px - g.x) * ax.y, ny = (py - g.y) * ax.y, nz = (pz - g.z) * ax.y;
+    float dn = fmaf(p.dz, nz, fmaf(p.dy, ny, p.dx * nx));
+    const bool front = dn < 0.0f;
+    if (!front) nx = -nx, ny = -ny, nz = -nz, dn = -dn;
+    const int type = __float_as_int(ax.w);
+    const uint32_t stream = p.bounce + 1u;  // stream 0 belongs to the camera ray
+    const uint4 r0 = philox4x32_10(k.pixel, k.sample, stream, 0u, k.k0, k.k1);
+    float ndx, ndy, ndz;
+    if (type == kDielectric) {
+        // Dielectric.scatter (src/material.zig:82-103)
+        const float ri = front ? al.w : ax.z;
+        const float cosT = fminf(-dn, 1.0f);
+        const float sinT = sqrtf(fmaf(-cosT, cosT, 1.0f));
+        const bool cannot = ri * sinT > 1.0f;
+        float q = (1.0f - ri) / (1.0f + ri);
+        q = q * q;
+        const float x = 1.0f - cosT;
+        const float x2 = x * x;
+        const float refl = fmaf(1.0f - q, x * (x2 * x2), q);  // Schlick (:106-110)
+        if (cannot || refl > u01(r0.x)) {
+            const float kk = -2.0f * dn;  // Vec.reflect (src/vec.zig:103-105)
+            ndx = fmaf(kk, nx, p.dx), ndy = fmaf(kk, ny, p.dy), ndz = fmaf(kk, nz, p.dz);
+        } else {  // Vec.refract (src/vec.zig:107-112)
+            const float ex = ri * fmaf(cosT, nx, p.dx), ey = ri * fmaf(cosT, ny, p.dy), ez = ri * fmaf(cosT, nz, p.dz);
+            const float kk = -sqrtf(fabsf(1.0f - fmaf(ez, ez, fmaf(ey, ey, ex * ex))));
+            ndx = fmaf(kk, nx, ex), ndy = fmaf(kk, ny, ey), ndz = fmaf(kk, nz, ez);
+        }
+    } else {
+        float ux, uy, uz;
+        random_unit_vec(k, stream, r0, ux, uy, uz);
+        if (type == kLambertian) {
+            // Lambertian.scatter (src/material.zig:27-39) incl. nearZero WITHOUT abs (Q1)
+            ndx = nx + ux, ndy = ny + uy, ndz = nz + uz;
+            if (ndx < 1e-8f && ndy < 1e-8f && ndz < 1e-8f) ndx = nx, ndy = ny, ndz = nz;
+        } else {
+            // Metal.scatter (src/material.zig:55-68): reflect + fuzz * unit vector; absorbed
+            // when the fuzzed direction points into the surface.  fuzz is not clamped (Q5).
+            const float kk = -2.0f * dn;
+            ndx = fmaf(ax.z, ux, fmaf(kk, nx, p.dx));
+            ndy = fmaf(ax.z, uy, fmaf(kk, ny, p.dy));
+            ndz = fmaf(ax.z, uz, fmaf(kk, nz, p.dz));
+            if (!(fmaf(ndz, nz, fmaf(ndy, ny, ndx * nx)) > 0.0f)) {
+                sr = sg = sb = 0.0f;
+                term = 1;
+                return true;
+            }
+        }
+        p.tr *= al.x, p.tg *= al.y, p.tb *= al.z;
+    }
+    p.bounce += 1u;
+    if (p.bounce >= cam.bounce_max) {  // src/camera.zig:153,181 (Q9)
+        sr = sg = sb = 0.0f;
+        term = 2;
+        return true;
+    }
+    p.ox = px, p.oy = py, p.oz = pz;
+    set_direction(p, ndx, ndy, ndz, cam.tmin);
+    p.self = best;
+    return false;
+}
+
+// Sample colour -> unsigned 32.32 fixed point.  Integer accumulation makes the pixel sum
+// independent of which lane / warp / GPU traced which sample.
+__device__ __forceinline__ unsigned long long to_fixed(float c) {
+    c = (c >= 0.0f) ? c : 0.0f;  // also maps NaN to 0
+    return __float2ull_rn(c * 4294967296.0f);
+}
+
+}  // namespace rtz

@@ -1,0 +1,417 @@
+// rtz_kernels.cuh — the kernels of librtz (sm_100a).
+//   K1 trace_kernel     : persistent path-trace megakernel (Camera.render's loop nest,
+//                         reference src/camera.zig:128-140 with rayColor :148-183 inlined)
+//   K2 legacy_kernel    : deterministic f64 primary-ray kernel for the chapter4/5/6 goldens
+//   K3 resolve_kernel   : 1/spp scale + gamma + clamp + 8-bit pack (src/camera.zig:137,
+//                         src/color.zig:63-80, src/ppm.zig:51-56)
+//   K4 deinterleave_kernel : rank-0 side of the multi-GPU tile gather
+//   probe kernels       : one-ray versions of sweep / shade / toRgb for the unit KATs
+//   ffma_peak_kernel    : FP32 pipe micro-benchmark for the roofline denominator
+#pragma once
+#include "rtz_device.cuh"
+
+namespace rtz {
+
+struct ShardGeom {
+    uint32_t rank, world, tile_w, tile_h, tiles_x, tiles_y, n_local_tiles, tile_pixels;
+};
+
+struct TraceParams {
+    DevCamera cam;
+    ShardGeom sh;
+    const float4* geom;     // [n_pad] {cx,cy,cz,r^2}
+    const float4* aux;      // [n_pad] {r, 1/r, fuzz|ior, type}
+    const float4* albedo;   // [n_pad] {r,g,b,1/ior}
+    int n_spheres;
+    int n_pad;              // n rounded up to a multiple of 4 (padding spheres can never be hit)
+    uint32_t chunk;         // samples per work chunk
+    uint32_t chunks_per_pixel;
+    uint64_t n_chunks;      // n_local_pixels(padded) * chunks_per_pixel
+    unsigned long long* accum;    // [n_local_pixels*3] 32.32 fixed-point colour sums
+    unsigned long long* counter;  // work-queue head
+    unsigned long long* stats;    // {samples, segments, depth_capped, absorbed}
+};
+
+// local (compact, padded) pixel index -> global pixel; false for tile padding
+__device__ __forceinline__ bool local_to_global(const ShardGeom& s, uint32_t W, uint32_t H, uint32_t lp, uint32_t& x,
+                                                uint32_t& y) {
+    const uint32_t lt = lp / s.tile_pixels, within = lp - lt * s.tile_pixels;
+    const uint32_t gt = lt * s.world + s.rank;
+    const uint32_t ty = gt / s.tiles_x, tx = gt - ty * s.tiles_x;
+    const uint32_t wy = within / s.tile_w, wx = within - wy * s.tile_w;
+    x = tx * s.tile_w + wx, y = ty * s.tile_h + wy;
+    return x < W && y < H && ty < s.tiles_y;
+}
+
+// --- 1-D TMA (cp.async.bulk) staging of the scene into shared memory ---------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t phase) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(phase)
+        : "memory");
+}
+
+// ---------------------------------------------------------------------------------------------
+// K1: persistent path-trace megakernel.
+//
+// Work = the rank's (pixel, sample) pairs, pixel-major, cut into chunks of <= P.chunk samples of
+// ONE pixel; chunks are handed out by a global atomic queue.  A warp keeps 32 paths in flight in
+// lockstep: every loop iteration is one world.hit for every live lane.  A lane whose path ended
+// takes the next sample of the warp's current chunk at once (path regeneration), so the sphere
+// sweep — 99 % of the work — always runs with full warps except while the queue drains.
+// Lanes add finished samples into private 32.32 fixed-point sums and flush them with 64-bit
+// integer atomics when they move to another pixel; integer addition commutes, so the image is
+// bit-identical for any schedule, tile size or GPU count.
+// ---------------------------------------------------------------------------------------------
+template <int kBlock>
+__global__ void __launch_bounds__(kBlock) trace_kernel(const __grid_constant__ TraceParams P) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    float4* s_geom = reinterpret_cast<float4*>(smem_raw);
+    float4* s_aux = s_geom + P.n_pad;
+    float4* s_alb = s_aux + P.n_pad;
+    __shared__ __align__(8) uint64_t s_bar;
+
+    if (threadIdx.x == 0) {
+        mbar_init(&s_bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const uint32_t bytes = (uint32_t)P.n_pad * 16u;
+        mbar_expect_tx(&s_bar, 3u * bytes);
+        bulk_g2s(s_geom, P.geom, bytes, &s_bar);
+        bulk_g2s(s_aux, P.aux, bytes, &s_bar);
+        bulk_g2s(s_alb, P.albedo, bytes, &s_bar);
+    }
+    mbar_wait(&s_bar, 0);
+
+    const unsigned lane = threadIdx.x & 31u;
+    const unsigned lt_mask = (1u << lane) - 1u;
+    const DevCamera& cam = P.cam;
+
+    Path path;
+    path.ox = path.oy = path.oz = 0.f, path.dx = path.dy = 0.f, path.dz = 1.f;
+    path.tr = path.tg = path.tb = 0.f, path.tmin_d = 0.f, path.self = -1, path.bounce = 0;
+    RngKey key{cam.key0, cam.key1, 0u, 0u};
+    bool alive = false;
+
+    uint32_t cur_lp = 0xFFFFFFFFu;  // pixel the private sums belong to
+    unsigned long long acc_r = 0, acc_g = 0, acc_b = 0;
+
+    // warp-uniform chunk state
+    uint32_t ch_lp = 0, ch_x = 0, ch_y = 0, ch_next = 0, ch_end = 0;
+    bool exhausted = false;
+
+    unsigned long long n_seg = 0;
+    uint32_t n_samp = 0, n_cap = 0, n_abs = 0;
+
+    for (;;) {
+        unsigned need = __ballot_sync(0xFFFFFFFFu, !alive);
+        if (need) {
+            while (need && !exhausted) {
+                if (ch_next >= ch_end) {
+                    unsigned long long cid = 0;
+                    if (lane == 0) cid = atomicAdd(P.counter, 1ULL);
+                    cid = __shfl_sync(0xFFFFFFFFu, cid, 0);
+                    if (cid >= P.n_chunks) {
+                        exhausted = true;
+                        break;
+                    }
+                    ch_lp = (uint32_t)(cid / P.chunks_per_pixel);
+                    const uint32_t part = (uint32_t)(cid - (unsigned long long)ch_lp * P.chunks_per_pixel);
+                    if (!local_to_global(P.sh, cam.width, cam.height, ch_lp, ch_x, ch_y)) continue;  // tile padding
+                    ch_next = part * P.chunk;
+                    ch_end = min(ch_next + P.chunk, cam.spp);
+                }
+                const uint32_t avail = ch_end - ch_next;
+                const uint32_t rank = __popc(need & lt_mask);
+                if (((need >> lane) & 1u) && rank < avail) {
+                    if (cur_lp != ch_lp) {
+                        if (cur_lp != 0xFFFFFFFFu && (acc_r | acc_g | acc_b)) {
+                            atomicAdd(P.accum + 3ull * cur_lp + 0, acc_r);
+                            atomicAdd(P.accum + 3ull * cur_lp + 1, acc_g);
+                            atomicAdd(P.accum + 3ull * cur_lp + 2, acc_b);
+                        }
+                        acc_r = acc_g = acc_b = 0;
+                        cur_lp = ch_lp;
+                    }
+                    key.pixel = ch_y * cam.width + ch_x;
+                    key.sample = ch_next + rank;
+                    camera_ray(cam, key, ch_x, ch_y, path);
+                    alive = true;
+                }
+                ch_next += min((uint32_t)__popc(need), avail);
+                need = __ballot_sync(0xFFFFFFFFu, !alive);
+            }
+            if (need == 0xFFFFFFFFu) break;  // queue drained and every path finished
+        }
+        if (alive) {
+            float t;
+            int best;
+            sweep(s_geom, P.n_pad, path, t, best);
+            ++n_seg;
+            float sr, sg, sb;
+            int term;
+            if (shade(cam, key, s_geom, s_aux, s_alb, path, t, best, sr, sg, sb, term)) {
+                acc_r += to_fixed(sr), acc_g += to_fixed(sg), acc_b += to_fixed(sb);
+                ++n_samp;
+                n_cap += (term == 2), n_abs += (term == 1);
+                alive = false;
+            }
+        }
+    }
+    if (cur_lp != 0xFFFFFFFFu && (acc_r | acc_g | acc_b)) {
+        atomicAdd(P.accum + 3ull * cur_lp + 0, acc_r);
+        atomicAdd(P.accum + 3ull * cur_lp + 1, acc_g);
+        atomicAdd(P.accum + 3ull * cur_lp + 2, acc_b);
+    }
+    // warp-reduce the work counters, one atomic per warp and counter
+    unsigned long long v0 = n_samp, v1 = n_seg, v2 = n_cap, v3 = n_abs;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        v0 += __shfl_xor_sync(0xFFFFFFFFu, v0, o);
+        v1 += __shfl_xor_sync(0xFFFFFFFFu, v1, o);
+        v2 += __shfl_xor_sync(0xFFFFFFFFu, v2, o);
+        v3 += __shfl_xor_sync(0xFFFFFFFFu, v3, o);
+    }
+    if (lane == 0) {
+        atomicAdd(P.stats + 0, v0);
+        atomicAdd(P.stats + 1, v1);
+        atomicAdd(P.stats + 2, v2);
+        atomicAdd(P.stats + 3, v3);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// K3: resolve.  pixelColor * pixelSamplesScale (src/camera.zig:137), then Color.toRgb
+// (src/color.zig:63-80): sqrt if > 0, clamp [0, .999], trunc(256 x).  f64 like the reference
+// (one sqrt per channel per pixel; the kernel is bound by its 27 B/pixel of HBM traffic).
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint8_t to_byte(double lin) {
+    double g = lin > 0.0 ? sqrt(lin) : 0.0;
+    g = g < 0.0 ? 0.0 : (g > 0.999 ? 0.999 : g);  // Interval.clamp (src/interval.zig:40-47)
+    return (uint8_t)(256.0 * g);
+}
+
+__global__ void resolve_kernel(const unsigned long long* __restrict__ accum, uint64_t n_pixels, double scale,
+                               uint8_t* __restrict__ rgb, double* __restrict__ linear) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;  // one thread per channel
+    if (i >= 3 * n_pixels) return;
+    const double lin = ((double)accum[i] * 0x1p-32) * scale;
+    rgb[i] = to_byte(lin);
+    if (linear) linear[i] = lin;
+}
+
+// ---------------------------------------------------------------------------------------------
+// K2: legacy deterministic pipelines behind test-files/chapter{4,5,6}.ppm.  f64, reference
+// operation order (the file is compiled with -fmad=false, so nothing is contracted): one ray
+// through the pixel centre, Sphere.hit as written (a = |d|^2 kept, division by a), no gamma,
+// trunc(255.999 c).
+// ---------------------------------------------------------------------------------------------
+struct DSphere {
+    double cx, cy, cz, r;
+};
+struct LegacyParams {
+    double p0[3], du[3], dv[3], c[3];
+    double tmin, tmax;
+    uint32_t width, height;
+    int mode;
+    int n;
+    const DSphere* spheres;
+};
+__device__ __forceinline__ double ddot(double ax, double ay, double az, double bx, double by, double bz) {
+    return (ax * bx + ay * by) + az * bz;
+}
+__global__ void legacy_kernel(const __grid_constant__ LegacyParams P, uint8_t* __restrict__ rgb,
+                              double* __restrict__ linear) {
+    const uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= P.width * P.height) return;
+    const uint32_t j = idx / P.width, i = idx - j * P.width;
+    const double fi = (double)i, fj = (double)j;
+    const double pcx = (P.p0[0] + P.du[0] * fi) + P.dv[0] * fj;
+    const double pcy = (P.p0[1] + P.du[1] * fi) + P.dv[1] * fj;
+    const double pcz = (P.p0[2] + P.du[2] * fi) + P.dv[2] * fj;
+    const double ox = P.c[0], oy = P.c[1], oz = P.c[2];
+    const double dx = pcx - ox, dy = pcy - oy, dz = pcz - oz;
+    bool hit = false;
+    double nx = 0, ny = 0, nz = 0;
+    if (P.mode != 1) {
+        double closest = P.tmax;
+        for (int s = 0; s < P.n; ++s) {
+            const DSphere sp = P.spheres[s];
+            const double ocx = sp.cx - ox, ocy = sp.cy - oy, ocz = sp.cz - oz;
+            const double a = ddot(dx, dy, dz, dx, dy, dz);
+            const double h = ddot(dx, dy, dz, ocx, ocy, ocz);
+            const double c = ddot(ocx, ocy, ocz, ocx, ocy, ocz) - sp.r * sp.r;
+            const double disc = h * h - a * c;
+            if (disc < 0) continue;
+            const double sq = sqrt(disc);
+            double root = (h - sq) / a;
+            if (!(P.tmin < root && root < closest)) {
+                root = (h + sq) / a;
+                if (!(P.tmin < root && root < closest)) continue;
+            }
+            closest = root;
+            hit = true;
+            const double px = ox + dx * root, py = oy + dy * root, pz = oz + dz * root;
+            const double inv = 1.0 / sp.r;  // divScalar = multiply by reciprocal (Q2)
+            nx = (px - sp.cx) * inv, ny = (py - sp.cy) * inv, nz = (pz - sp.cz) * inv;
+            if (!(ddot(dx, dy, dz, nx, ny, nz) < 0)) nx = -nx, ny = -ny, nz = -nz;
+        }
+    }
+    double r, g, b;
+    if (hit && P.mode == 2) {
+        r = 1, g = 0, b = 0;
+    } else if (hit) {
+        r = (nx + 1.0) * 0.5, g = (ny + 1.0) * 0.5, b = (nz + 1.0) * 0.5;
+    } else {
+        const double inv = 1.0 / sqrt(ddot(dx, dy, dz, dx, dy, dz));
+        const double a = 0.5 * (dy * inv + 1.0);
+        r = 1.0 * (1.0 - a) + 0.5 * a, g = 1.0 * (1.0 - a) + 0.7 * a, b = 1.0 * (1.0 - a) + 1.0 * a;
+    }
+    rgb[3 * idx + 0] = (uint8_t)(255.999 * r);
+    rgb[3 * idx + 1] = (uint8_t)(255.999 * g);
+    rgb[3 * idx + 2] = (uint8_t)(255.999 * b);
+    if (linear) linear[3 * idx + 0] = r, linear[3 * idx + 1] = g, linear[3 * idx + 2] = b;
+}
+
+// ---------------------------------------------------------------------------------------------
+// K4: de-interleave `world` equal-sized compact tile buffers into the row-major image.
+// ---------------------------------------------------------------------------------------------
+__global__ void deinterleave_kernel(const uint8_t* __restrict__ gathered, uint64_t per_rank_pixels, uint32_t W,
+                                    uint32_t H, uint32_t world, uint32_t tw, uint32_t th, uint32_t tiles_x,
+                                    uint8_t* __restrict__ out) {
+    const uint64_t idx = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (uint64_t)W * H) return;
+    const uint32_t y = (uint32_t)(idx / W), x = (uint32_t)(idx - (uint64_t)y * W);
+    const uint32_t tx = x / tw, ty = y / th;
+    const uint32_t gt = ty * tiles_x + tx;
+    const uint32_t rank = gt % world, lt = gt / world;
+    const uint64_t lp = (uint64_t)lt * (tw * th) + (y - ty * th) * tw + (x - tx * tw);
+    const uint8_t* src = gathered + 3ull * ((uint64_t)rank * per_rank_pixels + lp);
+    out[3 * idx + 0] = src[0], out[3 * idx + 1] = src[1], out[3 * idx + 2] = src[2];
+}
+
+// ---------------------------------------------------------------------------------------------
+// probes: one thread, the same device functions the render kernel inlines
+// ---------------------------------------------------------------------------------------------
+struct ProbeHitOut {
+    int hit, index, front;
+    float t, len;
+    float p[3], n[3];
+};
+__global__ void probe_hit_kernel(const float4* geom, const float4* aux, int n_pad, float ox, float oy, float oz,
+                                 float dx, float dy, float dz, float tmin, float tmax, ProbeHitOut* out) {
+    Path p;
+    p.ox = ox, p.oy = oy, p.oz = oz, p.self = -1, p.bounce = 0, p.tr = p.tg = p.tb = 1.f;
+    set_direction(p, dx, dy, dz, tmin);
+    const float len = sqrtf(fmaf(dz, dz, fmaf(dy, dy, dx * dx)));
+    float t;
+    int best;
+    sweep(geom, n_pad, p, t, best);
+    // the render kernel's t_max is +inf; a finite t_max (unit tests) is applied here
+    if (best >= 0 && !(t < tmax * len)) best = -1;
+    out->hit = best >= 0, out->index = best, out->len = len, out->t = t;
+    if (best >= 0) {
+        const float4 g = geom[best];
+        const float px = fmaf(t, p.dx, p.ox), py = fmaf(t, p.dy, p.oy), pz = fmaf(t, p.dz, p.oz);
+        float nx = (px - g.x) * aux[best].y, ny = (py - g.y) * aux[best].y, nz = (pz - g.z) * aux[best].y;
+        const bool front = fmaf(p.dz, nz, fmaf(p.dy, ny, p.dx * nx)) < 0.f;
+        if (!front) nx = -nx, ny = -ny, nz = -nz;
+        out->front = front, out->p[0] = px, out->p[1] = py, out->p[2] = pz, out->n[0] = nx, out->n[1] = ny, out->n[2] = nz;
+    }
+}
+
+struct ProbeScatterOut {
+    int scattered, term;
+    float o[3], d[3], att[3], len;
+};
+__global__ void probe_scatter_kernel(DevCamera cam, const float4* geom, const float4* aux, const float4* albedo,
+                                     int index, float ox, float oy, float oz, float dx, float dy, float dz,
+                                     uint32_t pixel, uint32_t sample, uint32_t bounce, ProbeScatterOut* out) {
+    Path p;
+    p.ox = ox, p.oy = oy, p.oz = oz, p.self = -1, p.bounce = bounce, p.tr = p.tg = p.tb = 1.f;
+    set_direction(p, dx, dy, dz, cam.tmin);
+    float t;
+    int best;
+    sweep(geom + index, 1, p, t, best);  // Sphere.hit on that one sphere
+    out->scattered = 0, out->term = -1;
+    if (best < 0) return;
+    RngKey k{cam.key0, cam.key1, pixel, sample};
+    float sr, sg, sb;
+    int term = -1;
+    const bool done = shade(cam, k, geom + index, aux + index, albedo + index, p, t, 0, sr, sg, sb, term);
+    out->term = term;
+    if (done) return;
+    out->scattered = 1;
+    out->o[0] = p.ox, out->o[1] = p.oy, out->o[2] = p.oz;
+    out->len = p.tmin_d / cam.tmin;  // |direction| before normalisation
+    out->d[0] = p.dx, out->d[1] = p.dy, out->d[2] = p.dz;
+    out->att[0] = p.tr, out->att[1] = p.tg, out->att[2] = p.tb;
+}
+
+__global__ void probe_to_rgb_kernel(const double* lin, uint64_t n3, uint8_t* out) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n3) out[i] = to_byte(lin[i]);
+}
+
+__global__ void probe_uniform_kernel(uint32_t k0, uint32_t k1, uint32_t pixel, uint32_t sample, uint32_t bounce,
+                                     uint64_t n, float* out) {
+    const uint64_t b = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (4 * b >= n) return;
+    const uint4 r = philox4x32_10(pixel, sample, bounce, (uint32_t)b, k0, k1);
+    const float v[4] = {u01(r.x), u01(r.y), u01(r.z), u01(r.w)};
+    for (int q = 0; q < 4 && 4 * b + q < n; ++q) out[4 * b + q] = v[q];
+}
+
+// ---------------------------------------------------------------------------------------------
+// FP32 pipe peak: independent FMA chains, no memory traffic.
+// ---------------------------------------------------------------------------------------------
+template <int kVariant>
+__global__ void __launch_bounds__(256) ffma_peak_kernel(float a, float b, int iters, float* sink) {
+    constexpr int C = 16;
+    float x[C];
+#pragma unroll
+    for (int i = 0; i < C; ++i) x[i] = (float)(threadIdx.x + i) * 1e-3f;
+    if (kVariant == 0) {
+        for (int it = 0; it < iters; ++it) {
+#pragma unroll
+            for (int i = 0; i < C; ++i) x[i] = fmaf(x[i], a, b);
+        }
+    } else {
+        float2 aa = make_float2(a, a), bb = make_float2(b, b);
+        for (int it = 0; it < iters; ++it) {
+#pragma unroll
+            for (int i = 0; i < C; i += 2) {
+                float2 v = __ffma2_rn(make_float2(x[i], x[i + 1]), aa, bb);
+                x[i] = v.x, x[i + 1] = v.y;
+            }
+        }
+    }
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < C; ++i) s += x[i];
+    if (s == 123.456f) *sink = s;
+}
+
+}  // namespace rtz

@@ -1,0 +1,319 @@
+"""Parity of the CUDA path (through the C ABI) against the oracle, on a real B200.
+
+Chain of custody for stochastic scenes:
+    GPU == oracle f32 mirror, bit for bit                      (this file)
+    mirror ~ f64 reference restatement, statistically           (test_oracle_stat.py, CPU)
+    f64 restatement == reference test-files/chapter14.ppm       (test_oracle_golden.py, CPU)
+Deterministic scenes: GPU bytes == reference test-files/chapter{4,5,6}.ppm, floats == oracle's.
+"""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import rtzlib as R
+
+pytestmark = pytest.mark.gpu
+
+
+def _mirror(orc, cam, sp, n, seed, shard=None, threads=8):
+    npix = cam.width * cam.height if shard is None else None
+    if shard is not None:
+        tiles_x = (cam.width + shard.tile_w - 1) // shard.tile_w
+        tiles_y = (cam.height + shard.tile_h - 1) // shard.tile_h
+        npix = ((tiles_x * tiles_y + shard.world - 1) // shard.world) * shard.tile_w * shard.tile_h
+    rgb = np.zeros((npix, 3), np.uint8)
+    lin = np.zeros((npix, 3), np.float64)
+    st = R.Stats()
+    rc = orc.orc_render_mirror(C.byref(cam), sp, n, seed, threads, C.byref(shard) if shard is not None else None,
+                               rgb.ctypes.data_as(C.POINTER(C.c_uint8)), lin.ctypes.data_as(C.POINTER(C.c_double)),
+                               C.byref(st))
+    assert rc == 0
+    return rgb, lin, st
+
+
+def _ulp_diff64(a, b):
+    ia = a.view(np.int64).astype(np.int64)
+    ib = b.view(np.int64).astype(np.int64)
+    return np.abs(ia - ib)
+
+
+# ------------------------------------------------------------------ deterministic goldens (C1)
+LEGACY = [
+    (R.MODE_LEGACY_SKY, "chapter4", []),
+    (R.MODE_LEGACY_FLAT, "chapter5", [((0, 0, -1), 0.5)]),
+    (R.MODE_LEGACY_NORMAL, "chapter6", [((0, 0, -1), 0.5), ((0, -100.5, -1), 100)]),
+]
+
+
+@pytest.mark.parametrize("mode,name,spheres", LEGACY)
+def test_deterministic_goldens_bit_exact(pkg, orc, mode, name, spheres):
+    cam = R.Camera()
+    orc.orc_camera_legacy(400, 16.0 / 9.0, mode, C.byref(cam))
+    sp = R.sphere_array([R.make_sphere(c, r, R.MAT_LAMBERTIAN) for c, r in spheres]) if spheres else (R.Sphere * 1)()
+    rgb, st, lin = pkg.render_host(cam, sp, len(spheres), want_linear=True)
+    w, h, body, _ = R.read_ppm(R.GOLDEN / f"{name}.ppm")
+    assert (w, h) == (cam.width, cam.height)
+    assert rgb.tobytes() == body, f"{name}: {np.count_nonzero(rgb.reshape(-1) != np.frombuffer(body, np.uint8))} bytes differ"
+    # floats before quantisation: the kernel computes in f64 in the reference's operation order
+    olin = np.zeros((h, w, 3), np.float64)
+    orgb = np.zeros((h, w, 3), np.uint8)
+    assert orc.orc_render_legacy(C.byref(cam), sp, len(spheres), orgb.ctypes.data_as(C.POINTER(C.c_uint8)),
+                                 olin.ctypes.data_as(C.POINTER(C.c_double)), None) == 0
+    assert _ulp_diff64(lin, olin).max() <= 1  # tolerance stated by north_star: 1 ULP
+    assert st.samples == w * h
+
+
+def test_legacy_file_bytes_identical(pkg, tmp_path):
+    """Camera.render's observable output is the P6 file: header + bytes + trailing newline."""
+    import rtzlib
+    cam = R.Camera()
+    rtzlib.oracle().orc_camera_legacy(400, 16.0 / 9.0, R.MODE_LEGACY_NORMAL, C.byref(cam))
+    sp = R.sphere_array([R.make_sphere((0, 0, -1), 0.5, 0), R.make_sphere((0, -100.5, -1), 100, 0)])
+    rgb, _ = pkg.render_host(cam, sp, 2)
+    out = tmp_path / "chapter6.ppm"
+    pkg.binding.check(pkg.lib().rtz_write_ppm(str(out).encode(), cam.width, cam.height,
+                                              rgb.ctypes.data_as(C.POINTER(C.c_uint8))))
+    assert out.read_bytes() == (R.GOLDEN / "chapter6.ppm").read_bytes()
+
+
+# ------------------------------------------------------------------ stochastic: GPU == mirror
+CH13_CAMERAS = {
+    "ch11": dict(look_from=(0, 0, 0), look_at=(0, 0, -1), vfov=90),
+    "ch12": dict(look_from=(-2, 2, 1), look_at=(0, 0, -1), vfov=20),
+    "ch13": dict(look_from=(-2, 2, 1), look_at=(0, 0, -1), vfov=20, defocus=10.0, viewport_focus=3.4, focus=3.4),
+}
+
+
+@pytest.mark.parametrize("preset", list(CH13_CAMERAS))
+def test_chapter13_scene_matches_mirror_bit_exact(gpu, orc, preset):
+    sp, n = R.chapter13_scene()
+    cam = R.build_camera(400, 16.0 / 9.0, spp=32, seed=0xDEADBEEF, **CH13_CAMERAS[preset])
+    gpu.upload(sp, n)
+    img, st = gpu.render(cam)
+    mrgb, mlin, mst = _mirror(orc, cam, sp, n, 0xDEADBEEF)
+    got = img.cpu().numpy().reshape(-1, 3)
+    assert (st.samples, st.segments, st.depth_capped, st.absorbed) == (
+        mst.samples, mst.segments, mst.depth_capped, mst.absorbed)
+    assert np.array_equal(got, mrgb), f"{np.count_nonzero(got != mrgb)} bytes differ"
+
+
+def test_final_scene_matches_mirror_bit_exact(pkg, gpu, orc):
+    prng, sp, n = R.final_scene(0xDEADBEEF)
+    assert n == 485
+    cam = R.main_camera(400, 10, seed=0xDEADBEEF)
+    # through the host-buffer C ABI, with the pre-quantisation floats
+    rgb, st, lin = pkg.render_host(cam, sp, n, want_linear=True)
+    mrgb, mlin, mst = _mirror(orc, cam, sp, n, 0xDEADBEEF)
+    assert st.samples == 400 * 225 * 10 == mst.samples
+    assert st.segments == mst.segments and st.depth_capped == mst.depth_capped and st.absorbed == mst.absorbed
+    assert st.sphere_tests == st.segments * 485
+    assert np.array_equal(lin.reshape(-1, 3), mlin)   # fixed-point sums agree exactly
+    assert np.array_equal(rgb.reshape(-1, 3), mrgb)
+    # and the resident path gives the same bytes
+    gpu.upload(sp, n)
+    img, st2 = gpu.render(cam)
+    assert np.array_equal(img.cpu().numpy(), rgb)
+    assert st2.segments == st.segments
+
+
+def test_seed_changes_image_and_is_reported(gpu):
+    sp, n = R.chapter13_scene()
+    gpu.upload(sp, n)
+    cam = R.build_camera(64, 16.0 / 9.0, (0, 0, 0), (0, 0, -1), 90, spp=4, seed=1)
+    a, sa = gpu.render(cam)
+    cam.seed = 2
+    b, sb = gpu.render(cam)
+    assert sa.seed_used == 1 and sb.seed_used == 2
+    assert not np.array_equal(a.cpu().numpy(), b.cpu().numpy())
+    cam.has_seed = 0  # Scene.init(null): key from the OS
+    c, sc = gpu.render(cam)
+    d, sd = gpu.render(cam)
+    assert sc.seed_used != sd.seed_used
+
+
+# ------------------------------------------------------------------ sharding: any world == 1 GPU
+@pytest.mark.parametrize("world,tile", [(2, (16, 16)), (3, (32, 8)), (8, (16, 16)), (4, (7, 5))])
+def test_interleaved_tiles_equal_whole_frame(pkg, gpu, orc, world, tile):
+    import torch
+    prng, sp, n = R.final_scene(0xDEADBEEF)
+    cam = R.main_camera(200, 6, seed=7)
+    gpu.upload(sp, n)
+    whole, st = gpu.render(cam)
+    parts, segs = [], 0
+    for rank in range(world):
+        sh = pkg.rtz_shard(rank, world, tile[0], tile[1])
+        part, pst = gpu.render(cam, sh)
+        parts.append(part)
+        segs += pst.segments
+        if rank == 1:  # one shard also against the mirror, incl. the padded pixels
+            msh = R.Shard(rank, world, tile[0], tile[1])
+            mrgb, _, mst = _mirror(orc, cam, sp, n, 7, msh)
+            assert np.array_equal(part.cpu().numpy(), mrgb)
+            assert pst.segments == mst.segments
+    gathered = torch.cat(parts, 0)
+    img = gpu.deinterleave(gathered, cam.width, cam.height, world, tile[0], tile[1])
+    assert torch.equal(img, whole)
+    assert segs == st.segments
+    # the host-side index map describes the same layout
+    per_rank, idx = pkg.tile_index_map(cam.width, cam.height, world, tile[0], tile[1])
+    assert per_rank == parts[0].shape[0]
+    assert np.array_equal(gathered.cpu().numpy()[idx.reshape(-1)].reshape(cam.height, cam.width, 3), whole.cpu().numpy())
+
+
+# ------------------------------------------------------------------ full-size properties (C3)
+def test_c3_full_size_properties(gpu):
+    prng, sp, n = R.final_scene(0xDEADBEEF)
+    cam = R.main_camera(1200, 500, seed=0xDEADBEEF)
+    assert (cam.width, cam.height) == (1200, 675)
+    gpu.upload(sp, n)
+    a, sa = gpu.render(cam)
+    b, sb = gpu.render(cam)
+    assert sa.samples == 1200 * 675 * 500
+    assert sa.sphere_tests == sa.segments * 485
+    # idempotence: dynamic scheduling must not leak into the image (integer accumulation)
+    assert np.array_equal(a.cpu().numpy(), b.cpu().numpy())
+    assert (sa.segments, sa.depth_capped, sa.absorbed) == (sb.segments, sb.depth_capped, sb.absorbed)
+    # work model: segments/sample within 2 % of the f64 oracle's 2.644, depth-cap <= 0.05 %
+    seg = sa.segments / sa.samples
+    assert abs(seg - 2.644) / 2.644 < 0.02, seg
+    assert sa.depth_capped / sa.samples <= 5e-4
+    # 500 spp converges to what 10 spp estimates: mean colour within sampling error
+    cam10 = R.main_camera(1200, 10, seed=99)
+    c, _ = gpu.render(cam10)
+    ma, mc = a.float().mean(dim=(0, 1)).cpu().numpy(), c.float().mean(dim=(0, 1)).cpu().numpy()
+    assert np.abs(ma - mc).max() < 1.0, (ma, mc)
+
+
+# ------------------------------------------------------------------ edge cases
+def test_edge_cases(pkg, gpu, orc):
+    l = pkg.lib()
+    sp, n = R.chapter13_scene()
+    # 1x1 image, 1 spp
+    cam = R.build_camera(1, 2.0, (0, 0, 0), (0, 0, -1), 90, spp=1, seed=3)
+    assert (cam.width, cam.height) == (1, 1)
+    rgb, st = pkg.render_host(cam, sp, n)
+    mrgb, _, mst = _mirror(orc, cam, sp, n, 3)
+    assert st.samples == 1 and np.array_equal(rgb.reshape(-1, 3), mrgb)
+    # bounce_max = 1: every hit that scatters is black (src/camera.zig:153,181)
+    cam = R.build_camera(96, 16.0 / 9.0, (0, 0, 0), (0, 0, -1), 90, spp=3, bounce_max=1, seed=3)
+    rgb, st = pkg.render_host(cam, sp, n)
+    mrgb, _, mst = _mirror(orc, cam, sp, n, 3)
+    assert st.segments == st.samples and np.array_equal(rgb.reshape(-1, 3), mrgb)
+    assert st.depth_capped == mst.depth_capped > 0
+    # odd sphere count (SoA padding), ragged width
+    cam = R.build_camera(37, 1.3, (-2, 2, 1), (0, 0, -1), 40, spp=5, seed=11)
+    rgb, st = pkg.render_host(cam, sp, 3)
+    mrgb, _, _ = _mirror(orc, cam, sp, 3, 11)
+    assert np.array_equal(rgb.reshape(-1, 3), mrgb)
+    # bad arguments fail loudly
+    st = pkg.rtz_stats()
+    bad = pkg.rtz_camera()
+    out = np.zeros(3, np.uint8).ctypes.data_as(C.POINTER(C.c_uint8))
+    assert l.rtz_render(C.byref(bad), C.cast(sp, C.POINTER(pkg.rtz_sphere)), n, out, C.byref(st)) == 1
+    assert l.rtz_render(None, None, 0, out, None) == 1
+
+
+def test_sphere_count_limits(pkg, gpu, orc):
+    # C5's largest scene (4096 spheres = 192 KiB of shared memory) renders and matches the mirror
+    prng = orc.orc_prng_new(0xDEADBEEF)
+    buf = (R.Sphere * 5000)()
+    assert orc.orc_generate_sweep(prng, 4096, buf) == 4096
+    cam = R.main_camera(64, 2, seed=5)
+    gpu.upload(buf, 4096)
+    img, st = gpu.render(cam)
+    mrgb, _, mst = _mirror(orc, cam, buf, 4096, 5)
+    assert st.sphere_tests == st.segments * 4096 and st.segments == mst.segments
+    assert np.array_equal(img.cpu().numpy().reshape(-1, 3), mrgb)
+    # one more doubling cannot be staged: explicit error, no fallback
+    big = (R.Sphere * 8192)()
+    for i in range(8192):
+        big[i] = buf[i % 4096]
+    gpu.upload(big, 8192)
+    with pytest.raises(pkg.RtzError) as e:
+        gpu.render(cam)
+    assert e.value.status == 5
+
+
+# ------------------------------------------------------------------ device unit KATs (reference unit tests)
+def test_probe_sphere_hit_kats(pkg):
+    """reference src/sphere.zig:76-136 and src/hittable.zig:185-209, on the device."""
+    l = pkg.lib()
+    one = R.sphere_array([R.make_sphere((0, 0, -2), 1, R.MAT_LAMBERTIAN)])
+    P = C.POINTER(pkg.rtz_sphere)
+    h = pkg.binding.rtz_hit()
+    assert l.rtz_probe_hit(C.cast(one, P), 1, R.d3((0, 0, 0)), R.d3((0, 0, -1)), 0.0, 3.0, C.byref(h)) == 0
+    assert h.hit == 1 and h.t == 1.0 and list(h.point) == [0, 0, -1] and list(h.normal) == [0, 0, 1] and h.front == 1
+    assert l.rtz_probe_hit(C.cast(one, P), 1, R.d3((0, 0, 0)), R.d3((0, 0, -1)), 0.0, 0.0, C.byref(h)) == 0
+    assert h.hit == 0  # empty interval
+    assert l.rtz_probe_hit(C.cast(one, P), 1, R.d3((0, 0, 0)), R.d3((0, 0, 1)), 0.0, 3.0, C.byref(h)) == 0
+    assert h.hit == 0  # pointing away
+    four = R.sphere_array([R.make_sphere((0, 0, -z), 1, R.MAT_LAMBERTIAN) for z in (2, 3, 4, 5)])
+    assert l.rtz_probe_hit(C.cast(four, P), 4, R.d3((0, 0, 0)), R.d3((0, 0, -1)), -6.0, 6.0, C.byref(h)) == 0
+    assert h.hit == 1 and h.index == 0 and h.t == 1.0 and list(h.normal) == [0, 0, 1]
+    # un-normalised direction: t is reported in units of |dir| like the reference
+    assert l.rtz_probe_hit(C.cast(one, P), 1, R.d3((0, 0, 0)), R.d3((0, 0, -4)), 0.0, 3.0, C.byref(h)) == 0
+    assert h.hit == 1 and h.t == 0.25
+
+
+def test_probe_scatter_kats(pkg, orc):
+    """reference src/material.zig:168-281."""
+    l = pkg.lib()
+    P = C.POINTER(pkg.rtz_sphere)
+    s = pkg.binding.rtz_scatter()
+    # metal, fuzz 0: direction == reflect(dir, normal) = (0,0,1); attenuation == albedo
+    metal = R.sphere_array([R.make_sphere((0, 0, -2), 1, R.MAT_METAL, albedo=(0.8, 0.6, 0.2), fuzz=0.0)])
+    assert l.rtz_probe_scatter(C.cast(metal, P), 1, 0, R.d3((0, 0, 0)), R.d3((0, 0, -1)), 1, 0, 0, 0, C.byref(s)) == 0
+    assert s.scattered == 1 and list(s.origin) == [0, 0, -1]
+    np.testing.assert_allclose(list(s.direction), [0, 0, 1], atol=1e-6)
+    np.testing.assert_allclose(list(s.attenuation), [0.8, 0.6, 0.2], rtol=1e-6)
+    # dielectric 1.5 head-on: reflectance 0.04, so (almost always) refract: direction keeps going -z
+    glass = R.sphere_array([R.make_sphere((0, 0, -2), 1, R.MAT_DIELECTRIC, ior=1.5)])
+    assert l.rtz_probe_scatter(C.cast(glass, P), 1, 0, R.d3((0, 0, 0)), R.d3((0, 0, -1)), 0xABADCAFE, 0, 0, 0,
+                               C.byref(s)) == 0
+    ref = R.D3()
+    orc.orc_vec_refract(R.d3((0, 0, -1)), R.d3((0, 0, 1)), 1 / 1.5, ref)
+    np.testing.assert_allclose(list(s.direction), list(ref), atol=1e-6)
+    assert list(s.attenuation) == [1, 1, 1]
+    # lambertian: direction = normal + unit vector -> |dir - normal| == 1; attenuation == albedo
+    lam = R.sphere_array([R.make_sphere((0, 0, -2), 1, R.MAT_LAMBERTIAN, albedo=(0.1, 0.2, 0.5))])
+    seen = set()
+    for smp in range(16):
+        assert l.rtz_probe_scatter(C.cast(lam, P), 1, 0, R.d3((0, 0, 0)), R.d3((0, 0, -1)), 5, 0, smp, 0, C.byref(s)) == 0
+        d = np.array(list(s.direction))
+        u = d - np.array([0, 0, 1.0])
+        q1 = (d < 1e-8).all()  # Q1: nearZero without abs replaces all-negative directions by the normal
+        assert q1 and np.allclose(d, [0, 0, 1]) or abs(np.linalg.norm(u) - 1) < 1e-5 or np.allclose(d, [0, 0, 1])
+        np.testing.assert_allclose(list(s.attenuation), [0.1, 0.2, 0.5], rtol=1e-6)
+        seen.add(tuple(np.round(d, 5)))
+    assert len(seen) > 8
+
+
+def test_probe_to_rgb_kats(pkg, orc):
+    """reference src/color.zig:131-135,157-172."""
+    l = pkg.lib()
+    lin = np.array([[0, .5, .75], [1, 0, 1], [-1, 0, 4], [0.999 ** 2, 1e-9, 0.25]], np.float64)
+    out = np.zeros((4, 3), np.uint8)
+    assert l.rtz_probe_to_rgb(lin.ctypes.data_as(C.POINTER(C.c_double)), 4, out.ctypes.data_as(C.POINTER(C.c_uint8))) == 0
+    assert out[0].tolist() == [0, 181, 221] and out[1].tolist() == [255, 0, 255] and out[2].tolist() == [0, 0, 255]
+    exp = np.zeros((4, 3), np.uint8)
+    orc.orc_to_rgb(lin.ctypes.data_as(C.POINTER(C.c_double)), 4, exp.ctypes.data_as(C.POINTER(C.c_uint8)))
+    assert np.array_equal(out, exp)
+
+
+def test_probe_uniform_matches_philox_oracle(pkg, orc):
+    l = pkg.lib()
+    got = np.zeros(1001, np.float32)
+    exp = np.zeros(1001, np.float32)
+    assert l.rtz_probe_uniform(0xDEADBEEF12345678, 17, 3, 2, 1001, got.ctypes.data_as(C.POINTER(C.c_float))) == 0
+    orc.orc_mirror_uniform.argtypes = [C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint64, C.POINTER(C.c_float)]
+    orc.orc_mirror_uniform(0xDEADBEEF12345678, 17, 3, 2, 1001, exp.ctypes.data_as(C.POINTER(C.c_float)))
+    assert np.array_equal(got, exp)
+    assert got.min() >= 0 and got.max() < 1 and 0.45 < got.mean() < 0.55
+
+
+def test_fp32_peak_microbenchmark(pkg):
+    l = pkg.lib()
+    v = C.c_double()
+    assert l.rtz_measure_fp32_peak(0, 0, C.byref(v)) == 0
+    assert 20 < v.value < 90, v.value  # nominal 74.4 TFLOP/s at 1965 MHz
