@@ -1,0 +1,80 @@
+"""The C-ABI library builds for sm_100a, loads without a GPU, exports every symbol include/rtz.h
+declares, and refuses to compute without a device (no CPU fallback)."""
+import ctypes as C
+import re
+import subprocess
+from pathlib import Path
+
+import rtzlib as R
+
+HEADER = R.ROOT / "include" / "rtz.h"
+
+
+def _declared():
+    text = re.sub(r"/\*.*?\*/", "", HEADER.read_text(), flags=re.S)
+    return sorted(set(re.findall(r"\b(rtz_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_exports_every_declared_symbol(pkg):
+    names = _declared()
+    assert len(names) >= 18 and "rtz_render" in names and "rtz_render_resident" in names
+    lib = C.CDLL(str(pkg.binding.LIB_PATH))
+    missing = [n for n in names if not hasattr(lib, n)]
+    assert not missing, missing
+    # the ctypes binding covers the same set
+    assert sorted(pkg.binding.SIGNATURES) == names
+    assert pkg.lib().rtz_abi_version() == 1
+
+
+def test_struct_layouts_match_header(pkg):
+    """extern-struct compatible PODs: sizes as a C compiler lays them out."""
+    src = r'''
+    #include <stdio.h>
+    #include "rtz.h"
+    int main(void){ printf("%zu %zu %zu %zu %zu %zu\n", sizeof(rtz_sphere), sizeof(rtz_camera), sizeof(rtz_shard),
+                           sizeof(rtz_stats), sizeof(rtz_hit), sizeof(rtz_scatter)); return 0; }
+    '''
+    import tempfile
+    with tempfile.TemporaryDirectory() as d:
+        (Path(d) / "s.c").write_text(src)
+        subprocess.run(["gcc", "-std=c99", "-I", str(HEADER.parent), "-o", f"{d}/s", f"{d}/s.c"], check=True)
+        sizes = [int(x) for x in subprocess.run([f"{d}/s"], capture_output=True, text=True, check=True).stdout.split()]
+    B = pkg.binding
+    assert sizes == [C.sizeof(B.rtz_sphere), C.sizeof(B.rtz_camera), C.sizeof(B.rtz_shard), C.sizeof(B.rtz_stats),
+                     C.sizeof(B.rtz_hit), C.sizeof(B.rtz_scatter)]
+    assert sizes == [C.sizeof(R.Sphere), C.sizeof(R.Camera), C.sizeof(R.Shard), C.sizeof(R.Stats), C.sizeof(R.Hit),
+                     C.sizeof(R.Scatter)]
+
+
+def test_sm100a_code_with_tma_in_the_binary(pkg):
+    """The shipped kernels are sm_100a SASS and the scene staging is a TMA bulk copy (UBLKCP)."""
+    out = subprocess.run(["cuobjdump", "-sass", str(pkg.binding.LIB_PATH)], capture_output=True, text=True).stdout
+    assert "sm_100a" in out
+    assert "UBLKCP" in out and "trace_kernel" in out
+
+
+def test_no_device_means_error_not_fallback(pkg):
+    import torch
+    if torch.cuda.is_available():
+        return  # covered by the gpu tests on a GPU box
+    l = pkg.lib()
+    n = C.c_int32(-1)
+    assert l.rtz_device_count(C.byref(n)) == 2 and n.value == 0  # RTZ_ERR_NO_DEVICE
+    sp, cnt = R.chapter13_scene()
+    cam = R.build_camera(8, 1.0, (0, 0, 0), (0, 0, -1), 90, spp=1, seed=1)
+    out = (C.c_uint8 * (3 * 64))()
+    bcam = pkg.rtz_camera.from_buffer_copy(bytes(cam))
+    rc = l.rtz_render(C.byref(bcam), C.cast(sp, C.POINTER(pkg.rtz_sphere)), cnt, out, None)
+    assert rc == 2 and b"no CUDA device" in l.rtz_strerror(rc)
+    try:
+        pkg.Renderer(0)
+        raise AssertionError("Renderer must refuse to run without a GPU")
+    except pkg.RtzError as e:
+        assert e.status == 2
+    # rtz_write_ppm is host-only I/O and works everywhere (PPM.saveBinary, src/ppm.zig:42-60)
+    import tempfile, os
+    with tempfile.TemporaryDirectory() as d:
+        p = os.path.join(d, "x.ppm").encode()
+        assert l.rtz_write_ppm(p, 1, 1, (C.c_uint8 * 3)()) == 0
+        assert open(p, "rb").read() == (R.GOLDEN / "test-binary.ppm").read_bytes()
+        assert l.rtz_write_ppm(os.path.join(d, "nodir", "x.ppm").encode(), 1, 1, (C.c_uint8 * 3)()) == 4
