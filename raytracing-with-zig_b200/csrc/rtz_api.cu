@@ -9,6 +9,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -402,15 +403,22 @@ int32_t rtz_deinterleave(rtz_context* c, uint64_t W, uint64_t H, uint32_t world,
     return RTZ_OK;
 }
 
+// The host-buffer entry points keep ONE lazily created context per process (buffers and stream are
+// reused from frame to frame; nothing of the caller's is retained).
+static std::mutex g_default_mu;
+static rtz_context* g_default_ctx = nullptr;
+
 int32_t rtz_render_linear(const rtz_camera* cam, const rtz_sphere* sp, uint64_t n, uint8_t* rgb_out,
                           double* linear_out, rtz_stats* st) {
     if (!rgb_out || (!sp && n)) return RTZ_ERR_BAD_ARG;
     int32_t rc = check_camera(cam);
     if (rc != RTZ_OK) return rc;
-    ScopedCtx sc;
-    rc = rtz_context_create(-1, nullptr, &sc.c);
-    if (rc != RTZ_OK) return rc;
-    rtz_context* c = sc.c;
+    std::lock_guard<std::mutex> lock(g_default_mu);
+    if (!g_default_ctx) {
+        rc = rtz_context_create(-1, nullptr, &g_default_ctx);
+        if (rc != RTZ_OK) return rc;
+    }
+    rtz_context* c = g_default_ctx;
     rc = rtz_scene_upload(c, sp, n);
     if (rc != RTZ_OK) return rc;
     const uint64_t px = cam->width * cam->height;

@@ -1,0 +1,70 @@
+"""ctypes view of host/librtz_host.so — the C++ mirror of the reference's host API
+(Scene.init/generateWorld/generateChapter13, Camera.builder(...).build(), main).  Product code:
+it links librtz.so and never the oracle."""
+from __future__ import annotations
+
+import ctypes as C
+from pathlib import Path
+
+from . import binding as B
+
+HOST_LIB = Path(__file__).resolve().parent / "host" / "librtz_host.so"
+_lib = None
+
+
+def hostlib() -> C.CDLL:
+    global _lib
+    if _lib is None:
+        if not HOST_LIB.exists():
+            raise ImportError(f"{HOST_LIB} is missing: run build.py (no fallback)")
+        B.lib()  # librtz.so first, so the dependency resolves from the in-tree copy
+        l = C.CDLL(str(HOST_LIB))
+        u64, i32, f64 = C.c_uint64, C.c_int32, C.c_double
+        l.rtzh_scene_generate_world.restype = u64
+        l.rtzh_scene_generate_world.argtypes = [u64, i32, C.POINTER(B.rtz_sphere), u64]
+        l.rtzh_scene_generate_chapter13.restype = u64
+        l.rtzh_scene_generate_chapter13.argtypes = [C.POINTER(B.rtz_sphere), u64]
+        l.rtzh_camera_build.restype = i32
+        l.rtzh_camera_build.argtypes = [u64, f64, B.D3, B.D3, B.D3, f64, f64, f64, u64, u64, u64, i32,
+                                        C.POINTER(B.rtz_camera)]
+        l.rtzh_main.restype = i32
+        l.rtzh_main.argtypes = [u64, u64, C.c_char_p, u64, i32, C.POINTER(B.rtz_stats)]
+        l.rtzh_list_hit.restype = i32
+        l.rtzh_list_hit.argtypes = [C.POINTER(B.rtz_sphere), u64, B.D3, B.D3, f64, f64, C.POINTER(B.rtz_hit)]
+        _lib = l
+    return _lib
+
+
+def generate_world(seed: int | None):
+    """Scene.init(seed).generateWorld() -> (rtz_sphere array, n).  485 spheres for 0xdeadbeef."""
+    buf = (B.rtz_sphere * 512)()
+    n = hostlib().rtzh_scene_generate_world(seed or 0, 0 if seed is None else 1, buf, 512)
+    return buf, int(n)
+
+
+def generate_chapter13():
+    buf = (B.rtz_sphere * 5)()
+    n = hostlib().rtzh_scene_generate_chapter13(buf, 5)
+    return buf, int(n)
+
+
+def camera_build(width, aspect, look_from, look_at, vfov, *, vup=(0, 1, 0), focus_dist=None, defocus_angle=0.0,
+                 spp=100, bounce_max=50, seed=None) -> B.rtz_camera:
+    cam = B.rtz_camera()
+    d3 = lambda v: B.D3(*[float(x) for x in v])
+    B.check(hostlib().rtzh_camera_build(width, aspect, d3(look_from), d3(look_at), d3(vup), vfov,
+                                        -1.0 if focus_dist is None else focus_dist, defocus_angle, spp, bounce_max,
+                                        seed or 0, 0 if seed is None else 1, C.byref(cam)))
+    return cam
+
+
+def main_camera(width: int, spp: int, seed=None) -> B.rtz_camera:
+    """The camera of reference src/main.zig:23-31."""
+    return camera_build(width, 16.0 / 9.0, (13, 2, 3), (0, 0, 0), 20, focus_dist=10.0, defocus_angle=0.6, spp=spp, seed=seed)
+
+
+def run_main(img_width: int, spp: int, file_name: str, seed=None):
+    """main(): renders to images/<file_name> under the current directory.  Returns rtz_stats."""
+    st = B.rtz_stats()
+    B.check(hostlib().rtzh_main(img_width, spp, file_name.encode(), seed or 0, 0 if seed is None else 1, C.byref(st)))
+    return st
