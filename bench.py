@@ -233,7 +233,7 @@ def run_ours(args, rank: int, world: int, local_rank: int):
         torch.cuda.synchronize()
         e2e_s = time.perf_counter() - t0
         e2e_samples = W * H * spp * args.steps
-        h2d = 3 * ((n + 3) // 4 * 4) * 16 + n * 32
+        h2d = 4 * ((n + 7) // 8 * 8) * 16 + n * 32
         d2h = W * H * 3 + 64
     else:
         host_img = torch.empty((H, W, 3), dtype=torch.uint8).pin_memory() if rank == 0 else None
@@ -251,7 +251,7 @@ def run_ours(args, rank: int, world: int, local_rank: int):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_s = t.item()
         e2e_samples = W * H * spp * args.steps
-        h2d = world * (3 * ((n + 3) // 4 * 4) * 16 + n * 32)
+        h2d = world * (4 * ((n + 7) // 8 * 8) * 16 + n * 32)
         d2h = W * H * 3 + world * 64
     e2e_value = e2e_samples / e2e_s / 1e6
 

@@ -166,7 +166,7 @@ int32_t render_path(rtz_context* ctx, const rtz_camera* cam, const rtz::ShardGeo
     P.accum = ctx->accum.p;
     P.counter = ctx->counters.p;
     P.stats = ctx->counters.p + 1;
-    const size_t smem = (size_t)ctx->n_pad * 48;
+    const size_t smem = (size_t)ctx->n_pad * 32;  // packed-pair geometry only; material rows stay in global/L1
     if (smem + 1024 > ctx->smem_optin) {
         g_last_error = "scene does not fit in shared memory";
         return RTZ_ERR_TOO_MANY_SPHERES;
@@ -324,30 +324,33 @@ int32_t rtz_context_destroy(rtz_context* c) {
 int32_t rtz_scene_upload(rtz_context* c, const rtz_sphere* sp, uint64_t n) {
     if (!c || (!sp && n) || n > (1u << 20)) return RTZ_ERR_BAD_ARG;
     RTZ_CUDA(cudaSetDevice(c->device));
-    const int n_pad = (int)((n + 3) & ~3ull);
-    std::vector<float4> g(n_pad), a(n_pad), al(n_pad);
+    const int n_pad = (int)((n + 7) & ~7ull);
+    std::vector<float4> g(2 * n_pad), a(n_pad), al(n_pad);
     std::vector<rtz::DSphere> ds(n ? n : 1);
     for (uint64_t i = 0; i < n; ++i) {
         const rtz_sphere& s = sp[i];
         if (s.mat_type < RTZ_MAT_LAMBERTIAN || s.mat_type > RTZ_MAT_DIELECTRIC) return RTZ_ERR_BAD_ARG;
         const float r = (float)(s.radius < 0 ? 0.0 : s.radius);  // Sphere.init clamp (src/sphere.zig:21)
-        g[i] = make_float4((float)s.center[0], (float)s.center[1], (float)s.center[2], r * r);
+        const float cx = (float)s.center[0], cy = (float)s.center[1], cz = (float)s.center[2];
+        g[2 * i] = make_float4(cx, cx, cy, cy);            // packed-pair layout for FFMA2 (two rays / thread)
+        g[2 * i + 1] = make_float4(cz, cz, -(r * r), -(r * r));
         const float param = s.mat_type == RTZ_MAT_METAL ? (float)s.fuzz : (float)s.refraction_index;
         a[i] = make_float4(r, 1.0f / r, param, bits_to_float(s.mat_type));
         al[i] = make_float4((float)s.albedo[0], (float)s.albedo[1], (float)s.albedo[2],
                             1.0f / (float)s.refraction_index);
         ds[i] = rtz::DSphere{s.center[0], s.center[1], s.center[2], s.radius < 0 ? 0.0 : s.radius};
     }
-    for (int i = (int)n; i < n_pad; ++i) {  // padding: r^2 = -inf makes the discriminant -inf
-        g[i] = make_float4(0.f, 0.f, 0.f, -INFINITY);
+    for (int i = (int)n; i < n_pad; ++i) {  // padding: -r^2 = +inf makes the discriminant -inf
+        g[2 * i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        g[2 * i + 1] = make_float4(0.f, 0.f, INFINITY, INFINITY);
         a[i] = make_float4(0.f, 0.f, 0.f, bits_to_float(0));
         al[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
     if (n_pad) {
-        RTZ_CUDA(c->geom.reserve(n_pad));
+        RTZ_CUDA(c->geom.reserve(2 * n_pad));
         RTZ_CUDA(c->aux.reserve(n_pad));
         RTZ_CUDA(c->albedo.reserve(n_pad));
-        RTZ_CUDA(cudaMemcpyAsync(c->geom.p, g.data(), n_pad * sizeof(float4), cudaMemcpyHostToDevice, c->stream));
+        RTZ_CUDA(cudaMemcpyAsync(c->geom.p, g.data(), 2 * n_pad * sizeof(float4), cudaMemcpyHostToDevice, c->stream));
         RTZ_CUDA(cudaMemcpyAsync(c->aux.p, a.data(), n_pad * sizeof(float4), cudaMemcpyHostToDevice, c->stream));
         RTZ_CUDA(cudaMemcpyAsync(c->albedo.p, al.data(), n_pad * sizeof(float4), cudaMemcpyHostToDevice, c->stream));
     }

@@ -19,11 +19,11 @@ struct ShardGeom {
 struct TraceParams {
     DevCamera cam;
     ShardGeom sh;
-    const float4* geom;     // [n_pad] {cx,cy,cz,r^2}
+    const float4* geom;     // [2*n_pad] packed-pair layout: {cx,cx,cy,cy},{cz,cz,-r^2,-r^2}
     const float4* aux;      // [n_pad] {r, 1/r, fuzz|ior, type}
     const float4* albedo;   // [n_pad] {r,g,b,1/ior}
     int n_spheres;
-    int n_pad;              // n rounded up to a multiple of 4 (padding spheres can never be hit)
+    int n_pad;              // n rounded up to a multiple of 8 (padding spheres can never be hit)
     uint32_t chunk;         // samples per work chunk
     uint32_t chunks_per_pixel;
     uint64_t n_chunks;      // n_local_pixels(padded) * chunks_per_pixel
@@ -75,20 +75,113 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t phase) {
 // K1: persistent path-trace megakernel.
 //
 // Work = the rank's (pixel, sample) pairs, pixel-major, cut into chunks of <= P.chunk samples of
-// ONE pixel; chunks are handed out by a global atomic queue.  A warp keeps 32 paths in flight in
-// lockstep: every loop iteration is one world.hit for every live lane.  A lane whose path ended
-// takes the next sample of the warp's current chunk at once (path regeneration), so the sphere
-// sweep — 99 % of the work — always runs with full warps except while the queue drains.
-// Lanes add finished samples into private 32.32 fixed-point sums and flush them with 64-bit
-// integer atomics when they move to another pixel; integer addition commutes, so the image is
-// bit-identical for any schedule, tile size or GPU count.
+// ONE pixel; chunks are handed out by a global atomic queue.  Every thread keeps TWO paths in
+// flight (slots A and B), so a warp advances 64 paths in lockstep: one loop iteration is one
+// world.hit for every live path.  A path that ended takes the next sample of the warp's current
+// chunk at once (path regeneration), so the sphere sweep — 99 % of the work — always runs with
+// full warps except while the queue drains.
+//
+// The sweep evaluates both paths of a thread with packed FP32x2 instructions (FADD2 / FMUL2 /
+// FFMA2, new on sm_100): per sphere 2 broadcast LDS.128 + 10 packed FP ops + 2 funnel shifts that
+// append the discriminants' sign bits to per-path candidate masks.  The FP32 pipe executes a
+// packed op in two passes, so the 10 packed ops (17 FLOP x 2 tests) are the floor and the other
+// 4 instructions issue in their shadow.  Roots are only evaluated for the mask's candidates, in
+// ascending sphere order, after each block of 32 spheres.
+//
+// Finished samples are converted to 32.32 fixed point and added to the pixel with 64-bit integer
+// REDs; integer addition commutes, so the image is bit-identical for any schedule, tile size or
+// GPU count.
 // ---------------------------------------------------------------------------------------------
+struct Slot {
+    Path path;
+    RngKey key;
+    uint32_t lp;  // local pixel (accumulator index)
+    bool alive;
+};
+
+// evaluate the candidates of one 32-sphere block for one path: Sphere.hit's root selection
+// (src/sphere.zig:35-42) with the shrinking t_max of HittableList.hit (src/hittable.zig:66-73)
+__device__ __forceinline__ void resolve_candidates(const float4* __restrict__ geo2, unsigned cand, int base, int cnt,
+                                                   const Path& p, float& closest, int& best) {
+    while (cand) {
+        const int bit = 31 - __clz(cand);  // highest bit = lowest sphere index: ascending order
+        cand &= ~(1u << bit);
+        const int i = base + (cnt - 1 - bit);
+        const float4 g0 = geo2[2 * i], g1 = geo2[2 * i + 1];
+        const float ocx = g0.x - p.ox, ocy = g0.z - p.oy, ocz = g1.x - p.oz;
+        const float h = fmaf(p.dz, ocz, fmaf(p.dy, ocy, p.dx * ocx));
+        const float c = fmaf(ocz, ocz, fmaf(ocy, ocy, fmaf(ocx, ocx, g1.z)));
+        const float disc = fmaf(h, h, -c);
+        slow_path(h, disc, i, p.self, p.tmin_d, closest, best);
+    }
+}
+
+// HittableList.hit for the two paths of a thread.  geo2[2i] = {cx,cx,cy,cy}, geo2[2i+1] =
+// {cz,cz,-r^2,-r^2}; n_pad is a multiple of 8 (padding spheres have -r^2 = +inf -> disc = -inf).
+__device__ __forceinline__ void sweep2(const float4* __restrict__ geo2, int n_pad, const Path& a, const Path& b,
+                                       float& ta, int& ia, float& tb, int& ib) {
+    const float2 nox = make_float2(-a.ox, -b.ox), noy = make_float2(-a.oy, -b.oy), noz = make_float2(-a.oz, -b.oz);
+    const float2 dx = make_float2(a.dx, b.dx), dy = make_float2(a.dy, b.dy), dz = make_float2(a.dz, b.dz);
+    float ca = __int_as_float(0x7f800000), cb = ca;
+    int ba = -1, bb = -1;
+    for (int base = 0; base < n_pad; base += 32) {
+        const int cnt = min(32, n_pad - base);
+        unsigned ma = 0xFFFFFFFFu, mb = 0xFFFFFFFFu;  // 1 = miss
+        const float4* g = geo2 + 2 * base;
+#pragma unroll 1
+        for (int k = 0; k < cnt; k += 8) {
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const float4 g0 = g[2 * (k + u)], g1 = g[2 * (k + u) + 1];
+                const float2 ocx = __fadd2_rn(make_float2(g0.x, g0.y), nox);
+                const float2 ocy = __fadd2_rn(make_float2(g0.z, g0.w), noy);
+                const float2 ocz = __fadd2_rn(make_float2(g1.x, g1.y), noz);
+                float2 h = __fmul2_rn(dx, ocx);
+                h = __ffma2_rn(dy, ocy, h);
+                h = __ffma2_rn(dz, ocz, h);
+                float2 c = __ffma2_rn(ocx, ocx, make_float2(g1.z, g1.w));
+                c = __ffma2_rn(ocy, ocy, c);
+                c = __ffma2_rn(ocz, ocz, c);
+                const float2 disc = __ffma2_rn(h, h, make_float2(-c.x, -c.y));
+                ma = __funnelshift_l(__float_as_uint(disc.x), ma, 1);  // append sign(disc)
+                mb = __funnelshift_l(__float_as_uint(disc.y), mb, 1);
+            }
+        }
+        const unsigned canda = ~ma, candb = ~mb;
+        if (canda | candb) {
+            resolve_candidates(geo2, canda, base, cnt, a, ca, ba);
+            resolve_candidates(geo2, candb, base, cnt, b, cb, bb);
+        }
+    }
+    ta = ca, ia = ba, tb = cb, ib = bb;
+}
+
+__device__ __forceinline__ void finish_or_continue(const TraceParams& P, const float4* s_geo2, const float4* s_aux,
+                                                   const float4* s_alb, Slot& s, float t, int best,
+                                                   unsigned long long& n_seg, uint32_t& n_samp, uint32_t& n_cap,
+                                                   uint32_t& n_abs) {
+    ++n_seg;
+    float sr, sg, sb;
+    int term;
+    if (shade(P.cam, s.key, s_geo2, s_aux, s_alb, s.path, t, best, sr, sg, sb, term)) {
+        const unsigned long long fr = to_fixed(sr), fg = to_fixed(sg), fb = to_fixed(sb);
+        unsigned long long* px = P.accum + 3ull * s.lp;
+        if (fr) atomicAdd(px + 0, fr);
+        if (fg) atomicAdd(px + 1, fg);
+        if (fb) atomicAdd(px + 2, fb);
+        ++n_samp;
+        n_cap += (term == 2), n_abs += (term == 1);
+        s.alive = false;
+    }
+}
+
 template <int kBlock>
 __global__ void __launch_bounds__(kBlock) trace_kernel(const __grid_constant__ TraceParams P) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    float4* s_geom = reinterpret_cast<float4*>(smem_raw);
-    float4* s_aux = s_geom + P.n_pad;
-    float4* s_alb = s_aux + P.n_pad;
+    float4* s_geo2 = reinterpret_cast<float4*>(smem_raw);  // [2*n_pad]: the only per-test data
+    // material rows are touched once per HIT (not per test): they stay in global memory / L1
+    const float4* s_aux = P.aux;
+    const float4* s_alb = P.albedo;
     __shared__ __align__(8) uint64_t s_bar;
 
     if (threadIdx.x == 0) {
@@ -98,10 +191,8 @@ __global__ void __launch_bounds__(kBlock) trace_kernel(const __grid_constant__ T
     __syncthreads();
     if (threadIdx.x == 0) {
         const uint32_t bytes = (uint32_t)P.n_pad * 16u;
-        mbar_expect_tx(&s_bar, 3u * bytes);
-        bulk_g2s(s_geom, P.geom, bytes, &s_bar);
-        bulk_g2s(s_aux, P.aux, bytes, &s_bar);
-        bulk_g2s(s_alb, P.albedo, bytes, &s_bar);
+        mbar_expect_tx(&s_bar, 2u * bytes);
+        bulk_g2s(s_geo2, P.geom, 2u * bytes, &s_bar);
     }
     mbar_wait(&s_bar, 0);
 
@@ -109,14 +200,13 @@ __global__ void __launch_bounds__(kBlock) trace_kernel(const __grid_constant__ T
     const unsigned lt_mask = (1u << lane) - 1u;
     const DevCamera& cam = P.cam;
 
-    Path path;
-    path.ox = path.oy = path.oz = 0.f, path.dx = path.dy = 0.f, path.dz = 1.f;
-    path.tr = path.tg = path.tb = 0.f, path.tmin_d = 0.f, path.self = -1, path.bounce = 0;
-    RngKey key{cam.key0, cam.key1, 0u, 0u};
-    bool alive = false;
-
-    uint32_t cur_lp = 0xFFFFFFFFu;  // pixel the private sums belong to
-    unsigned long long acc_r = 0, acc_g = 0, acc_b = 0;
+    Slot A, B;
+    A.alive = B.alive = false;
+    A.lp = B.lp = 0;
+    A.key = B.key = RngKey{cam.key0, cam.key1, 0u, 0u};
+    A.path.ox = A.path.oy = A.path.oz = 0.f, A.path.dx = A.path.dy = 0.f, A.path.dz = 1.f;
+    A.path.tr = A.path.tg = A.path.tb = 0.f, A.path.tmin_d = 0.f, A.path.self = -1, A.path.bounce = 0;
+    B.path = A.path;
 
     // warp-uniform chunk state
     uint32_t ch_lp = 0, ch_x = 0, ch_y = 0, ch_next = 0, ch_end = 0;
@@ -126,9 +216,10 @@ __global__ void __launch_bounds__(kBlock) trace_kernel(const __grid_constant__ T
     uint32_t n_samp = 0, n_cap = 0, n_abs = 0;
 
     for (;;) {
-        unsigned need = __ballot_sync(0xFFFFFFFFu, !alive);
-        if (need) {
-            while (need && !exhausted) {
+        unsigned need_a = __ballot_sync(0xFFFFFFFFu, !A.alive);
+        unsigned need_b = __ballot_sync(0xFFFFFFFFu, !B.alive);
+        if (need_a | need_b) {
+            while ((need_a | need_b) && !exhausted) {
                 if (ch_next >= ch_end) {
                     unsigned long long cid = 0;
                     if (lane == 0) cid = atomicAdd(P.counter, 1ULL);
@@ -144,46 +235,32 @@ __global__ void __launch_bounds__(kBlock) trace_kernel(const __grid_constant__ T
                     ch_end = min(ch_next + P.chunk, cam.spp);
                 }
                 const uint32_t avail = ch_end - ch_next;
-                const uint32_t rank = __popc(need & lt_mask);
-                if (((need >> lane) & 1u) && rank < avail) {
-                    if (cur_lp != ch_lp) {
-                        if (cur_lp != 0xFFFFFFFFu && (acc_r | acc_g | acc_b)) {
-                            atomicAdd(P.accum + 3ull * cur_lp + 0, acc_r);
-                            atomicAdd(P.accum + 3ull * cur_lp + 1, acc_g);
-                            atomicAdd(P.accum + 3ull * cur_lp + 2, acc_b);
-                        }
-                        acc_r = acc_g = acc_b = 0;
-                        cur_lp = ch_lp;
-                    }
-                    key.pixel = ch_y * cam.width + ch_x;
-                    key.sample = ch_next + rank;
-                    camera_ray(cam, key, ch_x, ch_y, path);
-                    alive = true;
+                const uint32_t na = __popc(need_a);
+                const uint32_t rank_a = __popc(need_a & lt_mask);
+                const uint32_t rank_b = na + __popc(need_b & lt_mask);
+                if (((need_a >> lane) & 1u) && rank_a < avail) {
+                    A.lp = ch_lp;
+                    A.key.pixel = ch_y * cam.width + ch_x, A.key.sample = ch_next + rank_a;
+                    camera_ray(cam, A.key, ch_x, ch_y, A.path);
+                    A.alive = true;
                 }
-                ch_next += min((uint32_t)__popc(need), avail);
-                need = __ballot_sync(0xFFFFFFFFu, !alive);
+                if (((need_b >> lane) & 1u) && rank_b < avail) {
+                    B.lp = ch_lp;
+                    B.key.pixel = ch_y * cam.width + ch_x, B.key.sample = ch_next + rank_b;
+                    camera_ray(cam, B.key, ch_x, ch_y, B.path);
+                    B.alive = true;
+                }
+                ch_next += min(na + (uint32_t)__popc(need_b), avail);
+                need_a = __ballot_sync(0xFFFFFFFFu, !A.alive);
+                need_b = __ballot_sync(0xFFFFFFFFu, !B.alive);
             }
-            if (need == 0xFFFFFFFFu) break;  // queue drained and every path finished
+            if ((need_a & need_b) == 0xFFFFFFFFu) break;  // queue drained and every path finished
         }
-        if (alive) {
-            float t;
-            int best;
-            sweep(s_geom, P.n_pad, path, t, best);
-            ++n_seg;
-            float sr, sg, sb;
-            int term;
-            if (shade(cam, key, s_geom, s_aux, s_alb, path, t, best, sr, sg, sb, term)) {
-                acc_r += to_fixed(sr), acc_g += to_fixed(sg), acc_b += to_fixed(sb);
-                ++n_samp;
-                n_cap += (term == 2), n_abs += (term == 1);
-                alive = false;
-            }
-        }
-    }
-    if (cur_lp != 0xFFFFFFFFu && (acc_r | acc_g | acc_b)) {
-        atomicAdd(P.accum + 3ull * cur_lp + 0, acc_r);
-        atomicAdd(P.accum + 3ull * cur_lp + 1, acc_g);
-        atomicAdd(P.accum + 3ull * cur_lp + 2, acc_b);
+        float ta, tb;
+        int ia, ib;
+        sweep2(s_geo2, P.n_pad, A.path, B.path, ta, ia, tb, ib);
+        if (A.alive) finish_or_continue(P, s_geo2, s_aux, s_alb, A, ta, ia, n_seg, n_samp, n_cap, n_abs);
+        if (B.alive) finish_or_continue(P, s_geo2, s_aux, s_alb, B, tb, ib, n_seg, n_samp, n_cap, n_abs);
     }
     // warp-reduce the work counters, one atomic per warp and counter
     unsigned long long v0 = n_samp, v1 = n_seg, v2 = n_cap, v3 = n_abs;
@@ -333,9 +410,9 @@ __global__ void probe_hit_kernel(const float4* geom, const float4* aux, int n_pa
     if (best >= 0 && !(t < tmax * len)) best = -1;
     out->hit = best >= 0, out->index = best, out->len = len, out->t = t;
     if (best >= 0) {
-        const float4 g = geom[best];
+        const float gx = geom[2 * best].x, gy = geom[2 * best].z, gz = geom[2 * best + 1].x;
         const float px = fmaf(t, p.dx, p.ox), py = fmaf(t, p.dy, p.oy), pz = fmaf(t, p.dz, p.oz);
-        float nx = (px - g.x) * aux[best].y, ny = (py - g.y) * aux[best].y, nz = (pz - g.z) * aux[best].y;
+        float nx = (px - gx) * aux[best].y, ny = (py - gy) * aux[best].y, nz = (pz - gz) * aux[best].y;
         const bool front = fmaf(p.dz, nz, fmaf(p.dy, ny, p.dx * nx)) < 0.f;
         if (!front) nx = -nx, ny = -ny, nz = -nz;
         out->front = front, out->p[0] = px, out->p[1] = py, out->p[2] = pz, out->n[0] = nx, out->n[1] = ny, out->n[2] = nz;
@@ -354,13 +431,13 @@ __global__ void probe_scatter_kernel(DevCamera cam, const float4* geom, const fl
     set_direction(p, dx, dy, dz, cam.tmin);
     float t;
     int best;
-    sweep(geom + index, 1, p, t, best);  // Sphere.hit on that one sphere
+    sweep(geom + 2 * index, 1, p, t, best);  // Sphere.hit on that one sphere
     out->scattered = 0, out->term = -1;
     if (best < 0) return;
     RngKey k{cam.key0, cam.key1, pixel, sample};
     float sr, sg, sb;
     int term = -1;
-    const bool done = shade(cam, k, geom + index, aux + index, albedo + index, p, t, 0, sr, sg, sb, term);
+    const bool done = shade(cam, k, geom + 2 * index, aux + index, albedo + index, p, t, 0, sr, sg, sb, term);
     out->term = term;
     if (done) return;
     out->scattered = 1;
