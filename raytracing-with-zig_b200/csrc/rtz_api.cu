@@ -72,9 +72,11 @@ struct rtz_context {
     bool own_stream = false;
     int sm_count = 0;
     size_t smem_optin = 0;
+    bool geo_const = false;  // RTZ_GEO_CONST=1: experimental constant-bank geometry kernel (default: TMA + shared memory)
     // scene (device SoA f32 + the f64 copy the legacy kernel reads)
     DevBuf<float4> geom, aux, albedo;
     DevBuf<rtz::DSphere> dspheres;
+    std::vector<float4> h_geom;
     int n_spheres = 0, n_pad = 0;
     // frame state
     DevBuf<unsigned long long> accum;
@@ -130,21 +132,20 @@ rtz::DevCamera to_dev_camera(const rtz_camera& c, uint64_t seed) {
 // chunk size: <= 256 samples of one pixel, and enough chunks to keep every warp busy
 uint32_t pick_chunk(uint32_t spp) { return spp < 256u ? spp : 256u; }
 
-template <int kBlock>
-int32_t launch_trace(rtz_context* ctx, const rtz::TraceParams& P, size_t smem) {
-    auto kern = rtz::trace_kernel<kBlock>;
-    RTZ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+template <class Kern, class Params>
+int32_t launch_trace(rtz_context* ctx, Kern kern, const Params& P, uint64_t n_chunks, int block, size_t smem) {
+    if (smem) RTZ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;
-    RTZ_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kBlock, smem));
+    RTZ_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, block, smem));
     if (per_sm < 1) {
         g_last_error = "scene does not fit in shared memory";
         return RTZ_ERR_TOO_MANY_SPHERES;
     }
-    const uint64_t warps_wanted = (P.n_chunks + 0) ;
+    // persistent grid: every SM full, but never more warps than chunks of work
     uint64_t blocks = (uint64_t)ctx->sm_count * per_sm;
-    const uint64_t max_useful = (warps_wanted + (kBlock / 32) - 1) / (kBlock / 32);
+    const uint64_t max_useful = (n_chunks + (block / 32) - 1) / (block / 32);
     if (blocks > max_useful) blocks = max_useful ? max_useful : 1;
-    kern<<<(unsigned)blocks, kBlock, smem, ctx->stream>>>(P);
+    kern<<<(unsigned)blocks, block, smem, ctx->stream>>>(P);
     RTZ_CUDA(cudaGetLastError());
     return RTZ_OK;
 }
@@ -166,7 +167,8 @@ int32_t render_path(rtz_context* ctx, const rtz_camera* cam, const rtz::ShardGeo
     P.accum = ctx->accum.p;
     P.counter = ctx->counters.p;
     P.stats = ctx->counters.p + 1;
-    const size_t smem = (size_t)ctx->n_pad * 32;  // packed-pair geometry only; material rows stay in global/L1
+    const bool use_const = ctx->n_pad <= rtz::kMaxConstSpheres && ctx->geo_const;
+    const size_t smem = use_const ? 0 : (size_t)(ctx->n_pad + 1) * 16;
     if (smem + 1024 > ctx->smem_optin) {
         g_last_error = "scene does not fit in shared memory";
         return RTZ_ERR_TOO_MANY_SPHERES;
@@ -175,7 +177,15 @@ int32_t render_path(rtz_context* ctx, const rtz_camera* cam, const rtz::ShardGeo
     RTZ_CUDA(cudaMemsetAsync(ctx->accum.p, 0, 3 * n_local_pixels * sizeof(unsigned long long), ctx->stream));
     RTZ_CUDA(cudaMemsetAsync(ctx->counters.p, 0, 8 * sizeof(unsigned long long), ctx->stream));
     RTZ_CUDA(cudaEventRecord(ctx->ev[1], ctx->stream));
-    int32_t rc = (smem > 96 * 1024) ? launch_trace<512>(ctx, P, smem) : launch_trace<256>(ctx, P, smem);
+    int32_t rc;
+    if (use_const) {
+        static thread_local rtz::TraceParamsConst C;  // 30 KiB: keep it off the stack
+        C.p = P;
+        std::memcpy(C.geo, ctx->h_geom.data(), (size_t)ctx->n_pad * sizeof(float4));
+        rc = launch_trace(ctx, rtz::trace_kernel_const<256>, C, P.n_chunks, 256, 0);
+    } else {
+        rc = launch_trace(ctx, rtz::trace_kernel_smem<256>, P, P.n_chunks, 256, smem);
+    }
     if (rc != RTZ_OK) return rc;
     RTZ_CUDA(cudaEventRecord(ctx->ev[2], ctx->stream));
     const uint64_t n3 = 3 * n_local_pixels;
@@ -285,6 +295,7 @@ int32_t rtz_context_create(int32_t device, void* stream, rtz_context** out) {
     c->device = device;
     c->sm_count = prop.multiProcessorCount;
     c->smem_optin = prop.sharedMemPerBlockOptin;
+    if (const char* e = std::getenv("RTZ_GEO_CONST")) c->geo_const = e[0] == '1';
     if (stream) {
         c->stream = (cudaStream_t)stream;
     } else {
@@ -325,32 +336,32 @@ int32_t rtz_scene_upload(rtz_context* c, const rtz_sphere* sp, uint64_t n) {
     if (!c || (!sp && n) || n > (1u << 20)) return RTZ_ERR_BAD_ARG;
     RTZ_CUDA(cudaSetDevice(c->device));
     const int n_pad = (int)((n + 7) & ~7ull);
-    std::vector<float4> g(2 * n_pad), a(n_pad), al(n_pad);
+    std::vector<float4> g(n_pad + 1), a(n_pad), al(n_pad);  // +1 padding sphere
     std::vector<rtz::DSphere> ds(n ? n : 1);
     for (uint64_t i = 0; i < n; ++i) {
         const rtz_sphere& s = sp[i];
         if (s.mat_type < RTZ_MAT_LAMBERTIAN || s.mat_type > RTZ_MAT_DIELECTRIC) return RTZ_ERR_BAD_ARG;
         const float r = (float)(s.radius < 0 ? 0.0 : s.radius);  // Sphere.init clamp (src/sphere.zig:21)
         const float cx = (float)s.center[0], cy = (float)s.center[1], cz = (float)s.center[2];
-        g[2 * i] = make_float4(cx, cx, cy, cy);            // packed-pair layout for FFMA2 (two rays / thread)
-        g[2 * i + 1] = make_float4(cz, cz, -(r * r), -(r * r));
+        g[i] = make_float4(cx, cy, cz, -(r * r));
         const float param = s.mat_type == RTZ_MAT_METAL ? (float)s.fuzz : (float)s.refraction_index;
         a[i] = make_float4(r, 1.0f / r, param, bits_to_float(s.mat_type));
         al[i] = make_float4((float)s.albedo[0], (float)s.albedo[1], (float)s.albedo[2],
                             1.0f / (float)s.refraction_index);
         ds[i] = rtz::DSphere{s.center[0], s.center[1], s.center[2], s.radius < 0 ? 0.0 : s.radius};
     }
-    for (int i = (int)n; i < n_pad; ++i) {  // padding: -r^2 = +inf makes the discriminant -inf
-        g[2 * i] = make_float4(0.f, 0.f, 0.f, 0.f);
-        g[2 * i + 1] = make_float4(0.f, 0.f, INFINITY, INFINITY);
-        a[i] = make_float4(0.f, 0.f, 0.f, bits_to_float(0));
-        al[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int i = (int)n; i < n_pad + 1; ++i) {  // padding: -r^2 = +inf makes the discriminant -inf
+        g[i] = make_float4(0.f, 0.f, 0.f, INFINITY);
+        if (i < n_pad) {
+            a[i] = make_float4(0.f, 0.f, 0.f, bits_to_float(0));
+            al[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
     }
     if (n_pad) {
-        RTZ_CUDA(c->geom.reserve(2 * n_pad));
+        RTZ_CUDA(c->geom.reserve(n_pad + 1));
         RTZ_CUDA(c->aux.reserve(n_pad));
         RTZ_CUDA(c->albedo.reserve(n_pad));
-        RTZ_CUDA(cudaMemcpyAsync(c->geom.p, g.data(), 2 * n_pad * sizeof(float4), cudaMemcpyHostToDevice, c->stream));
+        RTZ_CUDA(cudaMemcpyAsync(c->geom.p, g.data(), (n_pad + 1) * sizeof(float4), cudaMemcpyHostToDevice, c->stream));
         RTZ_CUDA(cudaMemcpyAsync(c->aux.p, a.data(), n_pad * sizeof(float4), cudaMemcpyHostToDevice, c->stream));
         RTZ_CUDA(cudaMemcpyAsync(c->albedo.p, al.data(), n_pad * sizeof(float4), cudaMemcpyHostToDevice, c->stream));
     }
@@ -358,6 +369,7 @@ int32_t rtz_scene_upload(rtz_context* c, const rtz_sphere* sp, uint64_t n) {
     RTZ_CUDA(cudaMemcpyAsync(c->dspheres.p, ds.data(), ds.size() * sizeof(rtz::DSphere), cudaMemcpyHostToDevice,
                              c->stream));
     RTZ_CUDA(cudaStreamSynchronize(c->stream));  // the staging vectors die here
+    c->h_geom = g;  // host copy: small scenes travel to the kernel as a __grid_constant__ parameter
     c->n_spheres = (int)n, c->n_pad = n_pad;
     return RTZ_OK;
 }

@@ -146,7 +146,7 @@ __device__ __forceinline__ void camera_ray(const DevCamera& c, const RngKey& k, 
 // ---------------------------------------------------------------------------------------------
 // HittableList.hit: brute-force closest hit over all spheres (src/hittable.zig:64-77), with
 // Sphere.hit's half-b quadratic (src/sphere.zig:26-43) for a unit direction.
-//   geo2[2i] = {cx, cx, cy, cy}, geo2[2i+1] = {cz, cz, -r^2, -r^2}   (packed-pair layout)
+//   geo[i] = {cx, cy, cz, -r^2}
 // Per test: 3 FADD + 1 FMUL + 6 FFMA = 17 FLOP.  The root is only evaluated when the
 // discriminant is non-negative.  This scalar form serves the one-ray probes; the render kernel
 // runs the same arithmetic two rays at a time (sweep2 in rtz_kernels.cuh).
@@ -164,17 +164,17 @@ __device__ __forceinline__ void slow_path(float h, float disc, int i, int self, 
     best = i;
 }
 
-__device__ __forceinline__ void sweep(const float4* __restrict__ geo2, int n, const Path& p, float& t_out,
+__device__ __forceinline__ void sweep(const float4* __restrict__ geo, int n, const Path& p, float& t_out,
                                       int& best_out) {
     float closest = __int_as_float(0x7f800000);  // +inf
     int best = -1;
     const float ox = p.ox, oy = p.oy, oz = p.oz, dx = p.dx, dy = p.dy, dz = p.dz;
 #pragma unroll 4
     for (int i = 0; i < n; ++i) {
-        const float4 g0 = geo2[2 * i], g1 = geo2[2 * i + 1];
-        const float ocx = g0.x - ox, ocy = g0.z - oy, ocz = g1.x - oz;
+        const float4 g = geo[i];
+        const float ocx = g.x - ox, ocy = g.y - oy, ocz = g.z - oz;
         const float h = fmaf(dz, ocz, fmaf(dy, ocy, dx * ocx));
-        const float c = fmaf(ocz, ocz, fmaf(ocy, ocy, fmaf(ocx, ocx, g1.z)));
+        const float c = fmaf(ocz, ocz, fmaf(ocy, ocy, fmaf(ocx, ocx, g.w)));
         const float disc = fmaf(h, h, -c);
         if (disc >= 0.0f) slow_path(h, disc, i, p.self, p.tmin_d, closest, best);
     }
@@ -188,7 +188,7 @@ __device__ __forceinline__ void sweep(const float4* __restrict__ geo2, int n, co
 //   aux[i]    = {r, 1/r, fuzz | ior, type bits}
 //   albedo[i] = {r, g, b, 1/ior}
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ bool shade(const DevCamera& cam, const RngKey& k, const float4* __restrict__ geo2,
+__device__ __forceinline__ bool shade(const DevCamera& cam, const RngKey& k, const float4* __restrict__ geo,
                                       const float4* __restrict__ aux, const float4* __restrict__ albedo, Path& p,
                                       float t, int best, float& sr, float& sg, float& sb, int& term) {
     if (best < 0) {
@@ -201,7 +201,8 @@ __device__ __forceinline__ bool shade(const DevCamera& cam, const RngKey& k, con
         term = 0;
         return true;
     }
-    const float gx = geo2[2 * best].x, gy = geo2[2 * best].z, gz = geo2[2 * best + 1].x;
+    const float4 gc = geo[best];
+    const float gx = gc.x, gy = gc.y, gz = gc.z;
     const float4 ax = __ldg(aux + best);
     const float4 al = __ldg(albedo + best);
     // HitRecord (src/sphere.zig:44-53)

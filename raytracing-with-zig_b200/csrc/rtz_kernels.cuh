@@ -19,7 +19,7 @@ struct ShardGeom {
 struct TraceParams {
     DevCamera cam;
     ShardGeom sh;
-    const float4* geom;     // [2*n_pad] packed-pair layout: {cx,cx,cy,cy},{cz,cz,-r^2,-r^2}
+    const float4* geom;     // [n_pad+1] {cx, cy, cz, -r^2}
     const float4* aux;      // [n_pad] {r, 1/r, fuzz|ior, type}
     const float4* albedo;   // [n_pad] {r,g,b,1/ior}
     int n_spheres;
@@ -30,6 +30,15 @@ struct TraceParams {
     unsigned long long* accum;    // [n_local_pixels*3] 32.32 fixed-point colour sums
     unsigned long long* counter;  // work-queue head
     unsigned long long* stats;    // {samples, segments, depth_capped, absorbed}
+};
+
+// Scenes of up to kMaxConstSpheres spheres travel as a __grid_constant__ kernel parameter: the
+// sweep then reads them through the constant bank with uniform loads (LDCU -> uniform registers
+// -> UR operands of FADD2/FFMA2), which needs no LDS, no vector registers and no shared memory.
+constexpr int kMaxConstSpheres = 1920;  // 30 KiB of the 32 KiB parameter space
+struct TraceParamsConst {
+    TraceParams p;
+    float4 geo[kMaxConstSpheres];
 };
 
 // local (compact, padded) pixel index -> global pixel; false for tile padding
@@ -100,26 +109,29 @@ struct Slot {
 };
 
 // evaluate the candidates of one 32-sphere block for one path: Sphere.hit's root selection
-// (src/sphere.zig:35-42) with the shrinking t_max of HittableList.hit (src/hittable.zig:66-73)
-__device__ __forceinline__ void resolve_candidates(const float4* __restrict__ geo2, unsigned cand, int base, int cnt,
+// (src/sphere.zig:35-42) with the shrinking t_max of HittableList.hit (src/hittable.zig:66-73).
+// `gather` is the copy of the geometry used for per-lane (divergent) lookups.
+__device__ __forceinline__ void resolve_candidates(const float4* __restrict__ gather, unsigned cand, int base, int cnt,
                                                    const Path& p, float& closest, int& best) {
     while (cand) {
         const int bit = 31 - __clz(cand);  // highest bit = lowest sphere index: ascending order
         cand &= ~(1u << bit);
         const int i = base + (cnt - 1 - bit);
-        const float4 g0 = geo2[2 * i], g1 = geo2[2 * i + 1];
-        const float ocx = g0.x - p.ox, ocy = g0.z - p.oy, ocz = g1.x - p.oz;
+        const float4 g = gather[i];
+        const float ocx = g.x - p.ox, ocy = g.y - p.oy, ocz = g.z - p.oz;
         const float h = fmaf(p.dz, ocz, fmaf(p.dy, ocy, p.dx * ocx));
-        const float c = fmaf(ocz, ocz, fmaf(ocy, ocy, fmaf(ocx, ocx, g1.z)));
+        const float c = fmaf(ocz, ocz, fmaf(ocy, ocy, fmaf(ocx, ocx, g.w)));
         const float disc = fmaf(h, h, -c);
         slow_path(h, disc, i, p.self, p.tmin_d, closest, best);
     }
 }
 
-// HittableList.hit for the two paths of a thread.  geo2[2i] = {cx,cx,cy,cy}, geo2[2i+1] =
-// {cz,cz,-r^2,-r^2}; n_pad is a multiple of 8 (padding spheres have -r^2 = +inf -> disc = -inf).
-__device__ __forceinline__ void sweep2(const float4* __restrict__ geo2, int n_pad, const Path& a, const Path& b,
-                                       float& ta, int& ia, float& tb, int& ib) {
+// HittableList.hit for the two paths of a thread.  geo[i] = {cx, cy, cz, -r^2}; every value is a
+// scalar-broadcast operand of the packed instruction (R.F32 / UR.F32).  n_pad is a multiple of 8
+// (padding spheres have -r^2 = +inf -> disc = -inf).  `geo` is warp-uniform storage: shared
+// memory (LDS.128) or the constant bank (LDCU); `gather` serves the per-lane lookups.
+__device__ __forceinline__ void sweep2(const float4* __restrict__ geo, const float4* __restrict__ gather, int n_pad,
+                                       const Path& a, const Path& b, float& ta, int& ia, float& tb, int& ib) {
     const float2 nox = make_float2(-a.ox, -b.ox), noy = make_float2(-a.oy, -b.oy), noz = make_float2(-a.oz, -b.oz);
     const float2 dx = make_float2(a.dx, b.dx), dy = make_float2(a.dy, b.dy), dz = make_float2(a.dz, b.dz);
     float ca = __int_as_float(0x7f800000), cb = ca;
@@ -127,19 +139,19 @@ __device__ __forceinline__ void sweep2(const float4* __restrict__ geo2, int n_pa
     for (int base = 0; base < n_pad; base += 32) {
         const int cnt = min(32, n_pad - base);
         unsigned ma = 0xFFFFFFFFu, mb = 0xFFFFFFFFu;  // 1 = miss
-        const float4* g = geo2 + 2 * base;
+        const float4* g = geo + base;
 #pragma unroll 1
         for (int k = 0; k < cnt; k += 8) {
 #pragma unroll
             for (int u = 0; u < 8; ++u) {
-                const float4 g0 = g[2 * (k + u)], g1 = g[2 * (k + u) + 1];
-                const float2 ocx = __fadd2_rn(make_float2(g0.x, g0.y), nox);
-                const float2 ocy = __fadd2_rn(make_float2(g0.z, g0.w), noy);
-                const float2 ocz = __fadd2_rn(make_float2(g1.x, g1.y), noz);
+                const float4 s = g[k + u];
+                const float2 ocx = __fadd2_rn(make_float2(s.x, s.x), nox);
+                const float2 ocy = __fadd2_rn(make_float2(s.y, s.y), noy);
+                const float2 ocz = __fadd2_rn(make_float2(s.z, s.z), noz);
                 float2 h = __fmul2_rn(dx, ocx);
                 h = __ffma2_rn(dy, ocy, h);
                 h = __ffma2_rn(dz, ocz, h);
-                float2 c = __ffma2_rn(ocx, ocx, make_float2(g1.z, g1.w));
+                float2 c = __ffma2_rn(ocx, ocx, make_float2(s.w, s.w));
                 c = __ffma2_rn(ocy, ocy, c);
                 c = __ffma2_rn(ocz, ocz, c);
                 const float2 disc = __ffma2_rn(h, h, make_float2(-c.x, -c.y));
@@ -149,21 +161,21 @@ __device__ __forceinline__ void sweep2(const float4* __restrict__ geo2, int n_pa
         }
         const unsigned canda = ~ma, candb = ~mb;
         if (canda | candb) {
-            resolve_candidates(geo2, canda, base, cnt, a, ca, ba);
-            resolve_candidates(geo2, candb, base, cnt, b, cb, bb);
+            resolve_candidates(gather, canda, base, cnt, a, ca, ba);
+            resolve_candidates(gather, candb, base, cnt, b, cb, bb);
         }
     }
     ta = ca, ia = ba, tb = cb, ib = bb;
 }
 
-__device__ __forceinline__ void finish_or_continue(const TraceParams& P, const float4* s_geo2, const float4* s_aux,
+__device__ __forceinline__ void finish_or_continue(const TraceParams& P, const float4* gather, const float4* s_aux,
                                                    const float4* s_alb, Slot& s, float t, int best,
                                                    unsigned long long& n_seg, uint32_t& n_samp, uint32_t& n_cap,
                                                    uint32_t& n_abs) {
     ++n_seg;
     float sr, sg, sb;
     int term;
-    if (shade(P.cam, s.key, s_geo2, s_aux, s_alb, s.path, t, best, sr, sg, sb, term)) {
+    if (shade(P.cam, s.key, gather, s_aux, s_alb, s.path, t, best, sr, sg, sb, term)) {
         const unsigned long long fr = to_fixed(sr), fg = to_fixed(sg), fb = to_fixed(sb);
         unsigned long long* px = P.accum + 3ull * s.lp;
         if (fr) atomicAdd(px + 0, fr);
@@ -175,27 +187,13 @@ __device__ __forceinline__ void finish_or_continue(const TraceParams& P, const f
     }
 }
 
-template <int kBlock>
-__global__ void __launch_bounds__(kBlock) trace_kernel(const __grid_constant__ TraceParams P) {
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    float4* s_geo2 = reinterpret_cast<float4*>(smem_raw);  // [2*n_pad]: the only per-test data
+// The body shared by the two kernels below.  `geo` is the warp-uniform geometry the sweep reads,
+// `gather` the copy for per-lane lookups (candidate roots, hit records).
+__device__ __forceinline__ void trace_body(const TraceParams& P, const float4* __restrict__ geo,
+                                           const float4* __restrict__ gather) {
     // material rows are touched once per HIT (not per test): they stay in global memory / L1
     const float4* s_aux = P.aux;
     const float4* s_alb = P.albedo;
-    __shared__ __align__(8) uint64_t s_bar;
-
-    if (threadIdx.x == 0) {
-        mbar_init(&s_bar, 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        const uint32_t bytes = (uint32_t)P.n_pad * 16u;
-        mbar_expect_tx(&s_bar, 2u * bytes);
-        bulk_g2s(s_geo2, P.geom, 2u * bytes, &s_bar);
-    }
-    mbar_wait(&s_bar, 0);
-
     const unsigned lane = threadIdx.x & 31u;
     const unsigned lt_mask = (1u << lane) - 1u;
     const DevCamera& cam = P.cam;
@@ -258,9 +256,9 @@ __global__ void __launch_bounds__(kBlock) trace_kernel(const __grid_constant__ T
         }
         float ta, tb;
         int ia, ib;
-        sweep2(s_geo2, P.n_pad, A.path, B.path, ta, ia, tb, ib);
-        if (A.alive) finish_or_continue(P, s_geo2, s_aux, s_alb, A, ta, ia, n_seg, n_samp, n_cap, n_abs);
-        if (B.alive) finish_or_continue(P, s_geo2, s_aux, s_alb, B, tb, ib, n_seg, n_samp, n_cap, n_abs);
+        sweep2(geo, gather, P.n_pad, A.path, B.path, ta, ia, tb, ib);
+        if (A.alive) finish_or_continue(P, gather, s_aux, s_alb, A, ta, ia, n_seg, n_samp, n_cap, n_abs);
+        if (B.alive) finish_or_continue(P, gather, s_aux, s_alb, B, tb, ib, n_seg, n_samp, n_cap, n_abs);
     }
     // warp-reduce the work counters, one atomic per warp and counter
     unsigned long long v0 = n_samp, v1 = n_seg, v2 = n_cap, v3 = n_abs;
@@ -277,6 +275,33 @@ __global__ void __launch_bounds__(kBlock) trace_kernel(const __grid_constant__ T
         atomicAdd(P.stats + 2, v2);
         atomicAdd(P.stats + 3, v3);
     }
+}
+
+// K1a: geometry in the constant bank (kernel parameter).  No shared memory at all.
+template <int kBlock>
+__global__ void __launch_bounds__(kBlock) trace_kernel_const(const __grid_constant__ TraceParamsConst C) {
+    trace_body(C.p, C.geo, C.p.geom);
+}
+
+// K1b: geometry staged into shared memory by one 1-D TMA bulk copy (cp.async.bulk + mbarrier);
+// for scenes too large for the parameter space (up to ~14 500 spheres in 227 KiB).
+template <int kBlock>
+__global__ void __launch_bounds__(kBlock) trace_kernel_smem(const __grid_constant__ TraceParams P) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    float4* s_geo = reinterpret_cast<float4*>(smem_raw);  // [n_pad + 1]
+    __shared__ __align__(8) uint64_t s_bar;
+    if (threadIdx.x == 0) {
+        mbar_init(&s_bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const uint32_t bytes = (uint32_t)(P.n_pad + 1) * 16u;
+        mbar_expect_tx(&s_bar, bytes);
+        bulk_g2s(s_geo, P.geom, bytes, &s_bar);
+    }
+    mbar_wait(&s_bar, 0);
+    trace_body(P, s_geo, s_geo);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -410,7 +435,7 @@ __global__ void probe_hit_kernel(const float4* geom, const float4* aux, int n_pa
     if (best >= 0 && !(t < tmax * len)) best = -1;
     out->hit = best >= 0, out->index = best, out->len = len, out->t = t;
     if (best >= 0) {
-        const float gx = geom[2 * best].x, gy = geom[2 * best].z, gz = geom[2 * best + 1].x;
+        const float gx = geom[best].x, gy = geom[best].y, gz = geom[best].z;
         const float px = fmaf(t, p.dx, p.ox), py = fmaf(t, p.dy, p.oy), pz = fmaf(t, p.dz, p.oz);
         float nx = (px - gx) * aux[best].y, ny = (py - gy) * aux[best].y, nz = (pz - gz) * aux[best].y;
         const bool front = fmaf(p.dz, nz, fmaf(p.dy, ny, p.dx * nx)) < 0.f;
@@ -431,13 +456,13 @@ __global__ void probe_scatter_kernel(DevCamera cam, const float4* geom, const fl
     set_direction(p, dx, dy, dz, cam.tmin);
     float t;
     int best;
-    sweep(geom + 2 * index, 1, p, t, best);  // Sphere.hit on that one sphere
+    sweep(geom + index, 1, p, t, best);  // Sphere.hit on that one sphere
     out->scattered = 0, out->term = -1;
     if (best < 0) return;
     RngKey k{cam.key0, cam.key1, pixel, sample};
     float sr, sg, sb;
     int term = -1;
-    const bool done = shade(cam, k, geom + 2 * index, aux + index, albedo + index, p, t, 0, sr, sg, sb, term);
+    const bool done = shade(cam, k, geom + index, aux + index, albedo + index, p, t, 0, sr, sg, sb, term);
     out->term = term;
     if (done) return;
     out->scattered = 1;

@@ -215,7 +215,7 @@ def test_edge_cases(pkg, gpu, orc):
 
 
 def test_sphere_count_limits(pkg, gpu, orc):
-    # C5's largest scene (4096 spheres = 192 KiB of shared memory) renders and matches the mirror
+    # C5's largest scene (4096 spheres = 64 KiB of shared memory) renders and matches the mirror
     prng = orc.orc_prng_new(0xDEADBEEF)
     buf = (R.Sphere * 5000)()
     assert orc.orc_generate_sweep(prng, 4096, buf) == 4096
@@ -225,11 +225,15 @@ def test_sphere_count_limits(pkg, gpu, orc):
     mrgb, _, mst = _mirror(orc, cam, buf, 4096, 5)
     assert st.sphere_tests == st.segments * 4096 and st.segments == mst.segments
     assert np.array_equal(img.cpu().numpy().reshape(-1, 3), mrgb)
-    # one more doubling cannot be staged: explicit error, no fallback
-    big = (R.Sphere * 8192)()
-    for i in range(8192):
+    # 16 B per sphere: 14 000 spheres still fit the 227 KiB of one SM ...
+    big = (R.Sphere * 16384)()
+    for i in range(16384):
         big[i] = buf[i % 4096]
-    gpu.upload(big, 8192)
+    gpu.upload(big, 14000)
+    img2, st2 = gpu.render(cam)
+    assert st2.sphere_tests == st2.segments * 14000
+    # ... 16 384 cannot be staged: explicit error, no fallback
+    gpu.upload(big, 16384)
     with pytest.raises(pkg.RtzError) as e:
         gpu.render(cam)
     assert e.value.status == 5
