@@ -4,8 +4,9 @@
 // reference functions as rtz_oracle.cpp (getRay, HittableList.hit, Sphere.hit, Material.scatter,
 // Color.toRgb — reference src/camera.zig:148-215, src/hittable.zig:64-77, src/sphere.zig:26-54,
 // src/material.zig:27-110, src/color.zig:63-80), but evaluated the way the B200 kernels
-// evaluate them: FP32, explicit fmaf, unit ray directions, hoisted |d|^2 and r^2, exact c = 0 for
-// the sphere the ray starts on, Philox4x32-10 keyed (seed; pixel, sample, bounce, block),
+// evaluate them: FP32, explicit fmaf, unit ray directions, candidate test on the discriminant
+// expanded around per-ray constants, roots from the direct form, exact c = 0 for the sphere the ray
+// starts on, Philox4x32-10 keyed (seed; pixel, sample, bounce, block),
 // Marsaglia unit vectors, 32.32 fixed-point pixel sums, f64 resolve.
 //
 // Because every operation is an IEEE-754 correctly rounded +,-,*,/,sqrt or fma, the GPU must
@@ -33,6 +34,7 @@ struct F3 {
 
 struct MSphere {  // the device SoA, one element
     float cx, cy, cz, r2;      // geom
+    float nq;                  // -(|c|^2 - r^2), evaluated in f64 on the FP32-rounded sphere
     float r, inv_r, param;     // aux (param = fuzz | ior)
     int type;
     float ar, ag, ab, inv_ior;  // albedo
@@ -118,8 +120,19 @@ inline void sweep(const std::vector<MSphere>& sp, const Path& p, float& t_out, i
     float closest = INFINITY;
     int best = -1;
     const int n = (int)sp.size();
+    // per-ray constants of the expanded discriminant
+    const float k1 = -std::fmaf(p.d.z, p.o.z, std::fmaf(p.d.y, p.o.y, p.d.x * p.o.x));
+    const float nk2 = -std::fmaf(p.o.z, p.o.z, std::fmaf(p.o.y, p.o.y, p.o.x * p.o.x));
+    const float tx = 2.0f * p.o.x, ty = 2.0f * p.o.y, tz = 2.0f * p.o.z;
     for (int i = 0; i < n; ++i) {
         const MSphere& s = sp[i];
+        // candidate test: h = d.c - d.o ; w = -(|c|^2 - r^2) - |o|^2 + 2 o.c ; disc = h^2 + w
+        const float he = std::fmaf(p.d.z, s.cz, std::fmaf(p.d.y, s.cy, std::fmaf(p.d.x, s.cx, k1)));
+        const float e = s.nq + nk2;
+        const float w = std::fmaf(tz, s.cz, std::fmaf(ty, s.cy, std::fmaf(tx, s.cx, e)));
+        const float de = std::fmaf(he, he, w);
+        if (std::signbit(de)) continue;
+        // root from the direct form (reference src/sphere.zig:27-42, unit direction)
         const float ocx = s.cx - p.o.x, ocy = s.cy - p.o.y, ocz = s.cz - p.o.z;
         const float h = std::fmaf(p.d.z, ocz, std::fmaf(p.d.y, ocy, p.d.x * ocx));
         const float c = std::fmaf(ocz, ocz, std::fmaf(ocy, ocy, std::fmaf(ocx, ocx, -s.r2)));
@@ -239,6 +252,7 @@ int orc_render_mirror(const rtz_camera* cam, const rtz_sphere* sp, uint64_t n, u
         MSphere& m = ms[i];
         const float r = (float)(s.radius < 0 ? 0.0 : s.radius);
         m.cx = (float)s.center[0], m.cy = (float)s.center[1], m.cz = (float)s.center[2], m.r2 = r * r;
+        m.nq = -(float)(((double)m.cx * m.cx + (double)m.cy * m.cy + (double)m.cz * m.cz) - (double)r * r);
         m.r = r, m.inv_r = 1.0f / r;
         m.param = s.mat_type == RTZ_MAT_METAL ? (float)s.fuzz : (float)s.refraction_index;
         m.type = s.mat_type;

@@ -75,6 +75,7 @@ struct rtz_context {
     bool geo_const = false;  // RTZ_GEO_CONST=1: experimental constant-bank geometry kernel (default: TMA + shared memory)
     // scene (device SoA f32 + the f64 copy the legacy kernel reads)
     DevBuf<float4> geom, aux, albedo;
+    DevBuf<float> nr2;
     DevBuf<rtz::DSphere> dspheres;
     std::vector<float4> h_geom;
     int n_spheres = 0, n_pad = 0;
@@ -159,7 +160,7 @@ int32_t render_path(rtz_context* ctx, const rtz_camera* cam, const rtz::ShardGeo
     rtz::TraceParams P;
     P.cam = to_dev_camera(*cam, seed);
     P.sh = sg;
-    P.geom = ctx->geom.p, P.aux = ctx->aux.p, P.albedo = ctx->albedo.p;
+    P.geom = ctx->geom.p, P.nr2 = ctx->nr2.p, P.aux = ctx->aux.p, P.albedo = ctx->albedo.p;
     P.n_spheres = ctx->n_spheres, P.n_pad = ctx->n_pad;
     P.chunk = pick_chunk(P.cam.spp);
     P.chunks_per_pixel = (P.cam.spp + P.chunk - 1) / P.chunk;
@@ -168,7 +169,7 @@ int32_t render_path(rtz_context* ctx, const rtz_camera* cam, const rtz::ShardGeo
     P.counter = ctx->counters.p;
     P.stats = ctx->counters.p + 1;
     const bool use_const = ctx->n_pad <= rtz::kMaxConstSpheres && ctx->geo_const;
-    const size_t smem = use_const ? 0 : (size_t)(ctx->n_pad + 1) * 16;
+    const size_t smem = use_const ? 0 : (size_t)(ctx->n_pad + 1) * 16 + (size_t)ctx->n_pad * 4;
     if (smem + 1024 > ctx->smem_optin) {
         g_last_error = "scene does not fit in shared memory";
         return RTZ_ERR_TOO_MANY_SPHERES;
@@ -322,7 +323,7 @@ int32_t rtz_context_destroy(rtz_context* c) {
     if (!c) return RTZ_ERR_BAD_ARG;
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
-    c->geom.release(), c->aux.release(), c->albedo.release(), c->dspheres.release();
+    c->geom.release(), c->aux.release(), c->albedo.release(), c->dspheres.release(), c->nr2.release();
     c->accum.release(), c->counters.release(), c->rgb.release(), c->linear.release();
     for (auto& e : c->ev)
         if (e) cudaEventDestroy(e);
@@ -337,13 +338,17 @@ int32_t rtz_scene_upload(rtz_context* c, const rtz_sphere* sp, uint64_t n) {
     RTZ_CUDA(cudaSetDevice(c->device));
     const int n_pad = (int)((n + 7) & ~7ull);
     std::vector<float4> g(n_pad + 1), a(n_pad), al(n_pad);  // +1 padding sphere
+    std::vector<float> nr2(n_pad ? n_pad : 1);
     std::vector<rtz::DSphere> ds(n ? n : 1);
     for (uint64_t i = 0; i < n; ++i) {
         const rtz_sphere& s = sp[i];
         if (s.mat_type < RTZ_MAT_LAMBERTIAN || s.mat_type > RTZ_MAT_DIELECTRIC) return RTZ_ERR_BAD_ARG;
         const float r = (float)(s.radius < 0 ? 0.0 : s.radius);  // Sphere.init clamp (src/sphere.zig:21)
         const float cx = (float)s.center[0], cy = (float)s.center[1], cz = (float)s.center[2];
-        g[i] = make_float4(cx, cy, cz, -(r * r));
+        // q = |c|^2 - r^2 of the FP32-rounded sphere, evaluated in f64 and rounded once
+        const double q = ((double)cx * cx + (double)cy * cy + (double)cz * cz) - (double)r * r;
+        g[i] = make_float4(cx, cy, cz, -(float)q);
+        nr2[i] = -(r * r);
         const float param = s.mat_type == RTZ_MAT_METAL ? (float)s.fuzz : (float)s.refraction_index;
         a[i] = make_float4(r, 1.0f / r, param, bits_to_float(s.mat_type));
         al[i] = make_float4((float)s.albedo[0], (float)s.albedo[1], (float)s.albedo[2],
@@ -351,7 +356,8 @@ int32_t rtz_scene_upload(rtz_context* c, const rtz_sphere* sp, uint64_t n) {
         ds[i] = rtz::DSphere{s.center[0], s.center[1], s.center[2], s.radius < 0 ? 0.0 : s.radius};
     }
     for (int i = (int)n; i < n_pad + 1; ++i) {  // padding: -r^2 = +inf makes the discriminant -inf
-        g[i] = make_float4(0.f, 0.f, 0.f, INFINITY);
+        g[i] = make_float4(0.f, 0.f, 0.f, -INFINITY);   // .w = -inf  ->  disc = -inf (never a candidate)
+        if (i < n_pad) nr2[i] = -0.f;
         if (i < n_pad) {
             a[i] = make_float4(0.f, 0.f, 0.f, bits_to_float(0));
             al[i] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -359,6 +365,8 @@ int32_t rtz_scene_upload(rtz_context* c, const rtz_sphere* sp, uint64_t n) {
     }
     if (n_pad) {
         RTZ_CUDA(c->geom.reserve(n_pad + 1));
+        RTZ_CUDA(c->nr2.reserve(n_pad));
+        RTZ_CUDA(cudaMemcpyAsync(c->nr2.p, nr2.data(), n_pad * sizeof(float), cudaMemcpyHostToDevice, c->stream));
         RTZ_CUDA(c->aux.reserve(n_pad));
         RTZ_CUDA(c->albedo.reserve(n_pad));
         RTZ_CUDA(cudaMemcpyAsync(c->geom.p, g.data(), (n_pad + 1) * sizeof(float4), cudaMemcpyHostToDevice, c->stream));
@@ -478,7 +486,7 @@ int32_t rtz_probe_hit(const rtz_sphere* sp, uint64_t n, const double o[3], const
     if (rc != RTZ_OK) return rc;
     rtz::ProbeHitOut* dout;
     RTZ_CUDA(cudaMalloc(&dout, sizeof(*dout)));
-    rtz::probe_hit_kernel<<<1, 1, 0, sc.c->stream>>>(sc.c->geom.p, sc.c->aux.p, sc.c->n_pad, (float)o[0], (float)o[1],
+    rtz::probe_hit_kernel<<<1, 1, 0, sc.c->stream>>>(sc.c->geom.p, sc.c->nr2.p, sc.c->aux.p, sc.c->n_pad, (float)o[0], (float)o[1],
                                                     (float)o[2], (float)d[0], (float)d[1], (float)d[2], (float)tmin,
                                                     (float)tmax, dout);
     rtz::ProbeHitOut h;
@@ -510,7 +518,7 @@ int32_t rtz_probe_scatter(const rtz_sphere* sp, uint64_t n, int32_t index, const
     const rtz::DevCamera dc = to_dev_camera(cam, seed);
     rtz::ProbeScatterOut* dout;
     RTZ_CUDA(cudaMalloc(&dout, sizeof(*dout)));
-    rtz::probe_scatter_kernel<<<1, 1, 0, sc.c->stream>>>(dc, sc.c->geom.p, sc.c->aux.p, sc.c->albedo.p, index,
+    rtz::probe_scatter_kernel<<<1, 1, 0, sc.c->stream>>>(dc, sc.c->geom.p, sc.c->nr2.p, sc.c->aux.p, sc.c->albedo.p, index,
                                                         (float)o[0], (float)o[1], (float)o[2], (float)d[0], (float)d[1],
                                                         (float)d[2], pixel, sample, bounce, dout);
     rtz::ProbeScatterOut h;

@@ -15,7 +15,12 @@
 // Differences from the reference's formulation, all distribution-preserving:
 //   * the ray direction is normalised once per segment (a = |d|^2 = 1 in Sphere.hit); t_min is
 //     rescaled by |d| so the (t_min, inf) interval keeps its reference meaning (Q7/Q8);
-//   * |d|^2 and r^2 are hoisted out of the sphere sweep (17 FLOP / test);
+//   * |d|^2 and r^2 are hoisted out of the sphere sweep (17 algorithmic FLOP / test);
+//   * the per-test miss/hit decision uses the discriminant expanded around per-ray constants,
+//         h = d.c - d.o ,   c' = (|c|^2 - r^2) - 2 c.o + |o|^2 ,   disc = h^2 - c'
+//     (8 fused ops per test instead of 10, and no 1e6-sized cancellation for the radius-1000
+//     ground sphere); the ROOT of a candidate is then computed from the reference's direct form
+//     oc = c - o, exactly as Sphere.hit writes it;
 //   * the sphere the ray starts on ("self") is intersected with c = |oc|^2 - r^2 := 0, the exact
 //     value, instead of the FP32-rounded one: this removes the self-intersection bias of a
 //     naive FP32 port (SURVEY §7 risk 5) without touching any other sphere;
@@ -146,10 +151,8 @@ __device__ __forceinline__ void camera_ray(const DevCamera& c, const RngKey& k, 
 // ---------------------------------------------------------------------------------------------
 // HittableList.hit: brute-force closest hit over all spheres (src/hittable.zig:64-77), with
 // Sphere.hit's half-b quadratic (src/sphere.zig:26-43) for a unit direction.
-//   geo[i] = {cx, cy, cz, -r^2}
-// Per test: 3 FADD + 1 FMUL + 6 FFMA = 17 FLOP.  The root is only evaluated when the
-// discriminant is non-negative.  This scalar form serves the one-ray probes; the render kernel
-// runs the same arithmetic two rays at a time (sweep2 in rtz_kernels.cuh).
+// Algorithmic cost per test: 17 FLOP (miss path of src/sphere.zig:27-33, |d|^2 and r^2 hoisted);
+// executed: 7 FFMA + 1 FADD on the expanded form.  The root is only evaluated for candidates.
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ void slow_path(float h, float disc, int i, int self, float tmin_d, float& closest,
                                           int& best) {
@@ -164,19 +167,47 @@ __device__ __forceinline__ void slow_path(float h, float disc, int i, int self, 
     best = i;
 }
 
-__device__ __forceinline__ void sweep(const float4* __restrict__ geo, int n, const Path& p, float& t_out,
-                                      int& best_out) {
+// per-ray constants of the expanded discriminant
+struct RayK {
+    float k1;             // -(d.o)
+    float nk2;            // -|o|^2
+    float tx, ty, tz;     // 2*o
+};
+__device__ __forceinline__ RayK ray_constants(const Path& p) {
+    RayK k;
+    k.k1 = -fmaf(p.dz, p.oz, fmaf(p.dy, p.oy, p.dx * p.ox));
+    k.nk2 = -fmaf(p.oz, p.oz, fmaf(p.oy, p.oy, p.ox * p.ox));
+    k.tx = 2.0f * p.ox, k.ty = 2.0f * p.oy, k.tz = 2.0f * p.oz;
+    return k;
+}
+// candidate test: sign of the expanded discriminant.  geo[i] = {cx, cy, cz, -(|c|^2 - r^2)}
+__device__ __forceinline__ float expanded_disc(const float4 g, const Path& p, const RayK& k) {
+    const float h = fmaf(p.dz, g.z, fmaf(p.dy, g.y, fmaf(p.dx, g.x, k.k1)));
+    const float e = g.w + k.nk2;
+    const float w = fmaf(k.tz, g.z, fmaf(k.ty, g.y, fmaf(k.tx, g.x, e)));
+    return fmaf(h, h, w);
+}
+// root of a candidate from the direct form (src/sphere.zig:27-42); nr2[i] = -r^2
+__device__ __forceinline__ void candidate_root(const float4 g, float nr2, int i, const Path& p, float& closest,
+                                               int& best) {
+    const float ocx = g.x - p.ox, ocy = g.y - p.oy, ocz = g.z - p.oz;
+    const float h = fmaf(p.dz, ocz, fmaf(p.dy, ocy, p.dx * ocx));
+    const float c = fmaf(ocz, ocz, fmaf(ocy, ocy, fmaf(ocx, ocx, nr2)));
+    const float disc = fmaf(h, h, -c);
+    if (disc >= 0.0f) slow_path(h, disc, i, p.self, p.tmin_d, closest, best);
+}
+
+// scalar sweep: serves the one-ray probes; the render kernel runs the same arithmetic two rays
+// at a time (sweep2 in rtz_kernels.cuh)
+__device__ __forceinline__ void sweep(const float4* __restrict__ geo, const float* __restrict__ nr2, int n,
+                                      const Path& p, float& t_out, int& best_out) {
     float closest = __int_as_float(0x7f800000);  // +inf
     int best = -1;
-    const float ox = p.ox, oy = p.oy, oz = p.oz, dx = p.dx, dy = p.dy, dz = p.dz;
-#pragma unroll 4
+    const RayK k = ray_constants(p);
     for (int i = 0; i < n; ++i) {
         const float4 g = geo[i];
-        const float ocx = g.x - ox, ocy = g.y - oy, ocz = g.z - oz;
-        const float h = fmaf(dz, ocz, fmaf(dy, ocy, dx * ocx));
-        const float c = fmaf(ocz, ocz, fmaf(ocy, ocy, fmaf(ocx, ocx, g.w)));
-        const float disc = fmaf(h, h, -c);
-        if (disc >= 0.0f) slow_path(h, disc, i, p.self, p.tmin_d, closest, best);
+        const float d = expanded_disc(g, p, k);
+        if (!(__float_as_uint(d) >> 31)) candidate_root(g, nr2[i], i, p, closest, best);
     }
     t_out = closest;
     best_out = best;

@@ -19,7 +19,8 @@ struct ShardGeom {
 struct TraceParams {
     DevCamera cam;
     ShardGeom sh;
-    const float4* geom;     // [n_pad+1] {cx, cy, cz, -r^2}
+    const float4* geom;     // [n_pad+1] {cx, cy, cz, -(|c|^2 - r^2)}
+    const float* nr2;       // [n_pad]   -r^2 (root of a candidate, direct form)
     const float4* aux;      // [n_pad] {r, 1/r, fuzz|ior, type}
     const float4* albedo;   // [n_pad] {r,g,b,1/ior}
     int n_spheres;
@@ -110,30 +111,30 @@ struct Slot {
 
 // evaluate the candidates of one 32-sphere block for one path: Sphere.hit's root selection
 // (src/sphere.zig:35-42) with the shrinking t_max of HittableList.hit (src/hittable.zig:66-73).
-// `gather` is the copy of the geometry used for per-lane (divergent) lookups.
-__device__ __forceinline__ void resolve_candidates(const float4* __restrict__ gather, unsigned cand, int base, int cnt,
-                                                   const Path& p, float& closest, int& best) {
+// `gather`/`nr2` are the copies of the geometry used for per-lane (divergent) lookups.
+__device__ __forceinline__ void resolve_candidates(const float4* __restrict__ gather, const float* __restrict__ nr2,
+                                                   unsigned cand, int base, int cnt, const Path& p, float& closest,
+                                                   int& best) {
     while (cand) {
         const int bit = 31 - __clz(cand);  // highest bit = lowest sphere index: ascending order
         cand &= ~(1u << bit);
         const int i = base + (cnt - 1 - bit);
-        const float4 g = gather[i];
-        const float ocx = g.x - p.ox, ocy = g.y - p.oy, ocz = g.z - p.oz;
-        const float h = fmaf(p.dz, ocz, fmaf(p.dy, ocy, p.dx * ocx));
-        const float c = fmaf(ocz, ocz, fmaf(ocy, ocy, fmaf(ocx, ocx, g.w)));
-        const float disc = fmaf(h, h, -c);
-        slow_path(h, disc, i, p.self, p.tmin_d, closest, best);
+        candidate_root(gather[i], nr2[i], i, p, closest, best);
     }
 }
 
-// HittableList.hit for the two paths of a thread.  geo[i] = {cx, cy, cz, -r^2}; every value is a
-// scalar-broadcast operand of the packed instruction (R.F32 / UR.F32).  n_pad is a multiple of 8
-// (padding spheres have -r^2 = +inf -> disc = -inf).  `geo` is warp-uniform storage: shared
-// memory (LDS.128) or the constant bank (LDCU); `gather` serves the per-lane lookups.
-__device__ __forceinline__ void sweep2(const float4* __restrict__ geo, const float4* __restrict__ gather, int n_pad,
-                                       const Path& a, const Path& b, float& ta, int& ia, float& tb, int& ib) {
-    const float2 nox = make_float2(-a.ox, -b.ox), noy = make_float2(-a.oy, -b.oy), noz = make_float2(-a.oz, -b.oz);
+// HittableList.hit for the two paths of a thread.  geo[i] = {cx, cy, cz, -(|c|^2-r^2)}; every
+// value is a scalar-broadcast operand of the packed instruction (R.F32 / UR.F32).  n_pad is a
+// multiple of 8 (padding spheres have .w = -inf -> disc = -inf).  `geo` is warp-uniform storage:
+// shared memory (LDS.128) or the constant bank; `gather`/`nr2` serve the per-lane lookups.
+// Per sphere and thread: 1 LDS.128 + 7 FFMA2 + 1 FADD2 + 2 SHF for TWO ray-sphere tests.
+__device__ __forceinline__ void sweep2(const float4* __restrict__ geo, const float4* __restrict__ gather,
+                                       const float* __restrict__ nr2, int n_pad, const Path& a, const Path& b,
+                                       float& ta, int& ia, float& tb, int& ib) {
+    const RayK ka = ray_constants(a), kb = ray_constants(b);
     const float2 dx = make_float2(a.dx, b.dx), dy = make_float2(a.dy, b.dy), dz = make_float2(a.dz, b.dz);
+    const float2 k1 = make_float2(ka.k1, kb.k1), nk2 = make_float2(ka.nk2, kb.nk2);
+    const float2 tx = make_float2(ka.tx, kb.tx), ty = make_float2(ka.ty, kb.ty), tz = make_float2(ka.tz, kb.tz);
     float ca = __int_as_float(0x7f800000), cb = ca;
     int ba = -1, bb = -1;
     for (int base = 0; base < n_pad; base += 32) {
@@ -145,24 +146,22 @@ __device__ __forceinline__ void sweep2(const float4* __restrict__ geo, const flo
 #pragma unroll
             for (int u = 0; u < 8; ++u) {
                 const float4 s = g[k + u];
-                const float2 ocx = __fadd2_rn(make_float2(s.x, s.x), nox);
-                const float2 ocy = __fadd2_rn(make_float2(s.y, s.y), noy);
-                const float2 ocz = __fadd2_rn(make_float2(s.z, s.z), noz);
-                float2 h = __fmul2_rn(dx, ocx);
-                h = __ffma2_rn(dy, ocy, h);
-                h = __ffma2_rn(dz, ocz, h);
-                float2 c = __ffma2_rn(ocx, ocx, make_float2(s.w, s.w));
-                c = __ffma2_rn(ocy, ocy, c);
-                c = __ffma2_rn(ocz, ocz, c);
-                const float2 disc = __ffma2_rn(h, h, make_float2(-c.x, -c.y));
+                float2 h = __ffma2_rn(dx, make_float2(s.x, s.x), k1);
+                h = __ffma2_rn(dy, make_float2(s.y, s.y), h);
+                h = __ffma2_rn(dz, make_float2(s.z, s.z), h);
+                float2 w = __fadd2_rn(make_float2(s.w, s.w), nk2);
+                w = __ffma2_rn(tx, make_float2(s.x, s.x), w);
+                w = __ffma2_rn(ty, make_float2(s.y, s.y), w);
+                w = __ffma2_rn(tz, make_float2(s.z, s.z), w);
+                const float2 disc = __ffma2_rn(h, h, w);
                 ma = __funnelshift_l(__float_as_uint(disc.x), ma, 1);  // append sign(disc)
                 mb = __funnelshift_l(__float_as_uint(disc.y), mb, 1);
             }
         }
         const unsigned canda = ~ma, candb = ~mb;
         if (canda | candb) {
-            resolve_candidates(gather, canda, base, cnt, a, ca, ba);
-            resolve_candidates(gather, candb, base, cnt, b, cb, bb);
+            resolve_candidates(gather, nr2, canda, base, cnt, a, ca, ba);
+            resolve_candidates(gather, nr2, candb, base, cnt, b, cb, bb);
         }
     }
     ta = ca, ia = ba, tb = cb, ib = bb;
@@ -190,7 +189,7 @@ __device__ __forceinline__ void finish_or_continue(const TraceParams& P, const f
 // The body shared by the two kernels below.  `geo` is the warp-uniform geometry the sweep reads,
 // `gather` the copy for per-lane lookups (candidate roots, hit records).
 __device__ __forceinline__ void trace_body(const TraceParams& P, const float4* __restrict__ geo,
-                                           const float4* __restrict__ gather) {
+                                           const float4* __restrict__ gather, const float* __restrict__ nr2) {
     // material rows are touched once per HIT (not per test): they stay in global memory / L1
     const float4* s_aux = P.aux;
     const float4* s_alb = P.albedo;
@@ -256,7 +255,7 @@ __device__ __forceinline__ void trace_body(const TraceParams& P, const float4* _
         }
         float ta, tb;
         int ia, ib;
-        sweep2(geo, gather, P.n_pad, A.path, B.path, ta, ia, tb, ib);
+        sweep2(geo, gather, nr2, P.n_pad, A.path, B.path, ta, ia, tb, ib);
         if (A.alive) finish_or_continue(P, gather, s_aux, s_alb, A, ta, ia, n_seg, n_samp, n_cap, n_abs);
         if (B.alive) finish_or_continue(P, gather, s_aux, s_alb, B, tb, ib, n_seg, n_samp, n_cap, n_abs);
     }
@@ -280,7 +279,7 @@ __device__ __forceinline__ void trace_body(const TraceParams& P, const float4* _
 // K1a: geometry in the constant bank (kernel parameter).  No shared memory at all.
 template <int kBlock>
 __global__ void __launch_bounds__(kBlock) trace_kernel_const(const __grid_constant__ TraceParamsConst C) {
-    trace_body(C.p, C.geo, C.p.geom);
+    trace_body(C.p, C.geo, C.p.geom, C.p.nr2);
 }
 
 // K1b: geometry staged into shared memory by one 1-D TMA bulk copy (cp.async.bulk + mbarrier);
@@ -288,7 +287,8 @@ __global__ void __launch_bounds__(kBlock) trace_kernel_const(const __grid_consta
 template <int kBlock>
 __global__ void __launch_bounds__(kBlock) trace_kernel_smem(const __grid_constant__ TraceParams P) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    float4* s_geo = reinterpret_cast<float4*>(smem_raw);  // [n_pad + 1]
+    float4* s_geo = reinterpret_cast<float4*>(smem_raw);               // [n_pad + 1]
+    float* s_nr2 = reinterpret_cast<float*>(s_geo + P.n_pad + 1);       // [n_pad]
     __shared__ __align__(8) uint64_t s_bar;
     if (threadIdx.x == 0) {
         mbar_init(&s_bar, 1);
@@ -296,12 +296,13 @@ __global__ void __launch_bounds__(kBlock) trace_kernel_smem(const __grid_constan
     }
     __syncthreads();
     if (threadIdx.x == 0) {
-        const uint32_t bytes = (uint32_t)(P.n_pad + 1) * 16u;
-        mbar_expect_tx(&s_bar, bytes);
+        const uint32_t bytes = (uint32_t)(P.n_pad + 1) * 16u, bytes2 = (uint32_t)P.n_pad * 4u;
+        mbar_expect_tx(&s_bar, bytes + bytes2);
         bulk_g2s(s_geo, P.geom, bytes, &s_bar);
+        bulk_g2s(s_nr2, P.nr2, bytes2, &s_bar);
     }
     mbar_wait(&s_bar, 0);
-    trace_body(P, s_geo, s_geo);
+    trace_body(P, s_geo, s_geo, s_nr2);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -422,7 +423,7 @@ struct ProbeHitOut {
     float t, len;
     float p[3], n[3];
 };
-__global__ void probe_hit_kernel(const float4* geom, const float4* aux, int n_pad, float ox, float oy, float oz,
+__global__ void probe_hit_kernel(const float4* geom, const float* nr2, const float4* aux, int n_pad, float ox, float oy, float oz,
                                  float dx, float dy, float dz, float tmin, float tmax, ProbeHitOut* out) {
     Path p;
     p.ox = ox, p.oy = oy, p.oz = oz, p.self = -1, p.bounce = 0, p.tr = p.tg = p.tb = 1.f;
@@ -430,7 +431,7 @@ __global__ void probe_hit_kernel(const float4* geom, const float4* aux, int n_pa
     const float len = sqrtf(fmaf(dz, dz, fmaf(dy, dy, dx * dx)));
     float t;
     int best;
-    sweep(geom, n_pad, p, t, best);
+    sweep(geom, nr2, n_pad, p, t, best);
     // the render kernel's t_max is +inf; a finite t_max (unit tests) is applied here
     if (best >= 0 && !(t < tmax * len)) best = -1;
     out->hit = best >= 0, out->index = best, out->len = len, out->t = t;
@@ -448,7 +449,8 @@ struct ProbeScatterOut {
     int scattered, term;
     float o[3], d[3], att[3], len;
 };
-__global__ void probe_scatter_kernel(DevCamera cam, const float4* geom, const float4* aux, const float4* albedo,
+__global__ void probe_scatter_kernel(DevCamera cam, const float4* geom, const float* nr2, const float4* aux,
+                                     const float4* albedo,
                                      int index, float ox, float oy, float oz, float dx, float dy, float dz,
                                      uint32_t pixel, uint32_t sample, uint32_t bounce, ProbeScatterOut* out) {
     Path p;
@@ -456,7 +458,7 @@ __global__ void probe_scatter_kernel(DevCamera cam, const float4* geom, const fl
     set_direction(p, dx, dy, dz, cam.tmin);
     float t;
     int best;
-    sweep(geom + index, 1, p, t, best);  // Sphere.hit on that one sphere
+    sweep(geom + index, nr2 + index, 1, p, t, best);  // Sphere.hit on that one sphere
     out->scattered = 0, out->term = -1;
     if (best < 0) return;
     RngKey k{cam.key0, cam.key1, pixel, sample};
