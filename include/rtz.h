@@ -216,7 +216,8 @@ int32_t rtz_device_count(int32_t* count_out);
 /* Measured FP32 pipe peak for the roofline denominator (SURVEY.md §8d asks for a measured
  * FFMA-chain figure next to the nominal 148*128*2*f_clk): runs an unrolled independent
  * FFMA-chain kernel on the device and returns TFLOP/s.  variant 0 = scalar FFMA,
- * 1 = packed FFMA2 (fma.rn.f32x2). */
+ * 1 = packed FFMA2 (fma.rn.f32x2), 2 = FFMA2 with a scalar-broadcast operand.  (The sweep loop's
+ * own ceiling is measured by tools/ubench/sweep_shapes.cu.) */
 int32_t rtz_measure_fp32_peak(int32_t device, int32_t variant, double* tflops_out);
 
 #ifdef __cplusplus

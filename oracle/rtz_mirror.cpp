@@ -126,10 +126,9 @@ inline void sweep(const std::vector<MSphere>& sp, const Path& p, float& t_out, i
     const float tx = 2.0f * p.o.x, ty = 2.0f * p.o.y, tz = 2.0f * p.o.z;
     for (int i = 0; i < n; ++i) {
         const MSphere& s = sp[i];
-        // candidate test: h = d.c - d.o ; w = -(|c|^2 - r^2) - |o|^2 + 2 o.c ; disc = h^2 + w
+        // candidate test: h = d.c - d.o ; w = (2 o.c - |o|^2) - (|c|^2 - r^2) ; disc = h^2 + w
         const float he = std::fmaf(p.d.z, s.cz, std::fmaf(p.d.y, s.cy, std::fmaf(p.d.x, s.cx, k1)));
-        const float e = s.nq + nk2;
-        const float w = std::fmaf(tz, s.cz, std::fmaf(ty, s.cy, std::fmaf(tx, s.cx, e)));
+        const float w = std::fmaf(tz, s.cz, std::fmaf(ty, s.cy, std::fmaf(tx, s.cx, nk2))) + s.nq;
         const float de = std::fmaf(he, he, w);
         if (std::signbit(de)) continue;
         // root from the direct form (reference src/sphere.zig:27-42, unit direction)

@@ -4,6 +4,7 @@
 // point needs a CUDA device and fails with RTZ_ERR_NO_DEVICE / RTZ_ERR_CUDA otherwise.
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <cerrno>
 #include <cmath>
 #include <cstdio>
@@ -72,12 +73,12 @@ struct rtz_context {
     bool own_stream = false;
     int sm_count = 0;
     size_t smem_optin = 0;
+    int variant = 0;
     bool geo_const = false;  // RTZ_GEO_CONST=1: experimental constant-bank geometry kernel (default: TMA + shared memory)
     // scene (device SoA f32 + the f64 copy the legacy kernel reads)
-    DevBuf<float4> geom, aux, albedo;
-    DevBuf<float> nr2;
+    DevBuf<float4> geom, pairs, aux, albedo;
     DevBuf<rtz::DSphere> dspheres;
-    std::vector<float4> h_geom;
+    std::vector<float4> h_pairs;
     int n_spheres = 0, n_pad = 0;
     // frame state
     DevBuf<unsigned long long> accum;
@@ -160,7 +161,7 @@ int32_t render_path(rtz_context* ctx, const rtz_camera* cam, const rtz::ShardGeo
     rtz::TraceParams P;
     P.cam = to_dev_camera(*cam, seed);
     P.sh = sg;
-    P.geom = ctx->geom.p, P.nr2 = ctx->nr2.p, P.aux = ctx->aux.p, P.albedo = ctx->albedo.p;
+    P.geom = ctx->geom.p, P.pairs = ctx->pairs.p, P.aux = ctx->aux.p, P.albedo = ctx->albedo.p;
     P.n_spheres = ctx->n_spheres, P.n_pad = ctx->n_pad;
     P.chunk = pick_chunk(P.cam.spp);
     P.chunks_per_pixel = (P.cam.spp + P.chunk - 1) / P.chunk;
@@ -169,7 +170,7 @@ int32_t render_path(rtz_context* ctx, const rtz_camera* cam, const rtz::ShardGeo
     P.counter = ctx->counters.p;
     P.stats = ctx->counters.p + 1;
     const bool use_const = ctx->n_pad <= rtz::kMaxConstSpheres && ctx->geo_const;
-    const size_t smem = use_const ? 0 : (size_t)(ctx->n_pad + 1) * 16 + (size_t)ctx->n_pad * 4;
+    const size_t smem = use_const ? 0 : (size_t)ctx->n_pad * 32;  // pair layout + per-lane rows
     if (smem + 1024 > ctx->smem_optin) {
         g_last_error = "scene does not fit in shared memory";
         return RTZ_ERR_TOO_MANY_SPHERES;
@@ -182,10 +183,16 @@ int32_t render_path(rtz_context* ctx, const rtz_camera* cam, const rtz::ShardGeo
     if (use_const) {
         static thread_local rtz::TraceParamsConst C;  // 30 KiB: keep it off the stack
         C.p = P;
-        std::memcpy(C.geo, ctx->h_geom.data(), (size_t)ctx->n_pad * sizeof(float4));
+        std::memcpy(C.pairs, ctx->h_pairs.data(), (size_t)ctx->n_pad * sizeof(float4));
         rc = launch_trace(ctx, rtz::trace_kernel_const<256>, C, P.n_chunks, 256, 0);
     } else {
-        rc = launch_trace(ctx, rtz::trace_kernel_smem<256>, P, P.n_chunks, 256, smem);
+        switch (ctx->variant) {  // RTZ_VARIANT: launch-shape experiments; 0 = the measured best
+            case 1: rc = launch_trace(ctx, rtz::trace_kernel_smem<256, 2>, P, P.n_chunks, 256, smem); break;
+            case 2: rc = launch_trace(ctx, rtz::trace_kernel_smem<256, 3>, P, P.n_chunks, 256, smem); break;
+            case 3: rc = launch_trace(ctx, rtz::trace_kernel_smem<128, 4>, P, P.n_chunks, 128, smem); break;
+            case 4: rc = launch_trace(ctx, rtz::trace_kernel_smem<128, 6>, P, P.n_chunks, 128, smem); break;
+            default: rc = launch_trace(ctx, rtz::trace_kernel_smem<128, 5>, P, P.n_chunks, 128, smem); break;
+        }
     }
     if (rc != RTZ_OK) return rc;
     RTZ_CUDA(cudaEventRecord(ctx->ev[2], ctx->stream));
@@ -297,6 +304,7 @@ int32_t rtz_context_create(int32_t device, void* stream, rtz_context** out) {
     c->sm_count = prop.multiProcessorCount;
     c->smem_optin = prop.sharedMemPerBlockOptin;
     if (const char* e = std::getenv("RTZ_GEO_CONST")) c->geo_const = e[0] == '1';
+    if (const char* e = std::getenv("RTZ_VARIANT")) c->variant = std::atoi(e);
     if (stream) {
         c->stream = (cudaStream_t)stream;
     } else {
@@ -323,7 +331,7 @@ int32_t rtz_context_destroy(rtz_context* c) {
     if (!c) return RTZ_ERR_BAD_ARG;
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
-    c->geom.release(), c->aux.release(), c->albedo.release(), c->dspheres.release(), c->nr2.release();
+    c->geom.release(), c->pairs.release(), c->aux.release(), c->albedo.release(), c->dspheres.release();
     c->accum.release(), c->counters.release(), c->rgb.release(), c->linear.release();
     for (auto& e : c->ev)
         if (e) cudaEventDestroy(e);
@@ -337,8 +345,8 @@ int32_t rtz_scene_upload(rtz_context* c, const rtz_sphere* sp, uint64_t n) {
     if (!c || (!sp && n) || n > (1u << 20)) return RTZ_ERR_BAD_ARG;
     RTZ_CUDA(cudaSetDevice(c->device));
     const int n_pad = (int)((n + 7) & ~7ull);
-    std::vector<float4> g(n_pad + 1), a(n_pad), al(n_pad);  // +1 padding sphere
-    std::vector<float> nr2(n_pad ? n_pad : 1);
+    std::vector<float4> g(n_pad ? n_pad : 1), pr(n_pad ? n_pad : 1), a(n_pad ? n_pad : 1), al(n_pad ? n_pad : 1);
+    std::vector<float> w(n_pad ? n_pad : 1);
     std::vector<rtz::DSphere> ds(n ? n : 1);
     for (uint64_t i = 0; i < n; ++i) {
         const rtz_sphere& s = sp[i];
@@ -347,29 +355,32 @@ int32_t rtz_scene_upload(rtz_context* c, const rtz_sphere* sp, uint64_t n) {
         const float cx = (float)s.center[0], cy = (float)s.center[1], cz = (float)s.center[2];
         // q = |c|^2 - r^2 of the FP32-rounded sphere, evaluated in f64 and rounded once
         const double q = ((double)cx * cx + (double)cy * cy + (double)cz * cz) - (double)r * r;
-        g[i] = make_float4(cx, cy, cz, -(float)q);
-        nr2[i] = -(r * r);
+        g[i] = make_float4(cx, cy, cz, -(r * r));
+        w[i] = -(float)q;
         const float param = s.mat_type == RTZ_MAT_METAL ? (float)s.fuzz : (float)s.refraction_index;
         a[i] = make_float4(r, 1.0f / r, param, bits_to_float(s.mat_type));
         al[i] = make_float4((float)s.albedo[0], (float)s.albedo[1], (float)s.albedo[2],
                             1.0f / (float)s.refraction_index);
         ds[i] = rtz::DSphere{s.center[0], s.center[1], s.center[2], s.radius < 0 ? 0.0 : s.radius};
     }
-    for (int i = (int)n; i < n_pad + 1; ++i) {  // padding: -r^2 = +inf makes the discriminant -inf
-        g[i] = make_float4(0.f, 0.f, 0.f, -INFINITY);   // .w = -inf  ->  disc = -inf (never a candidate)
-        if (i < n_pad) nr2[i] = -0.f;
-        if (i < n_pad) {
-            a[i] = make_float4(0.f, 0.f, 0.f, bits_to_float(0));
-            al[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-        }
+    for (int i = (int)n; i < n_pad; ++i) {  // padding: w = -inf  ->  disc = -inf (never a candidate)
+        g[i] = make_float4(0.f, 0.f, 0.f, -0.f);
+        w[i] = -INFINITY;
+        a[i] = make_float4(0.f, 0.f, 0.f, bits_to_float(0));
+        al[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    for (int p = 0; p < n_pad / 2; ++p) {  // sweep layout: one FFMA2 = one ray x the two spheres of a pair
+        const float4 A = g[2 * p], B = g[2 * p + 1];
+        pr[2 * p] = make_float4(A.x, B.x, A.y, B.y);
+        pr[2 * p + 1] = make_float4(A.z, B.z, w[2 * p], w[2 * p + 1]);
     }
     if (n_pad) {
-        RTZ_CUDA(c->geom.reserve(n_pad + 1));
-        RTZ_CUDA(c->nr2.reserve(n_pad));
-        RTZ_CUDA(cudaMemcpyAsync(c->nr2.p, nr2.data(), n_pad * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+        RTZ_CUDA(c->geom.reserve(n_pad));
+        RTZ_CUDA(c->pairs.reserve(n_pad));
         RTZ_CUDA(c->aux.reserve(n_pad));
         RTZ_CUDA(c->albedo.reserve(n_pad));
-        RTZ_CUDA(cudaMemcpyAsync(c->geom.p, g.data(), (n_pad + 1) * sizeof(float4), cudaMemcpyHostToDevice, c->stream));
+        RTZ_CUDA(cudaMemcpyAsync(c->geom.p, g.data(), n_pad * sizeof(float4), cudaMemcpyHostToDevice, c->stream));
+        RTZ_CUDA(cudaMemcpyAsync(c->pairs.p, pr.data(), n_pad * sizeof(float4), cudaMemcpyHostToDevice, c->stream));
         RTZ_CUDA(cudaMemcpyAsync(c->aux.p, a.data(), n_pad * sizeof(float4), cudaMemcpyHostToDevice, c->stream));
         RTZ_CUDA(cudaMemcpyAsync(c->albedo.p, al.data(), n_pad * sizeof(float4), cudaMemcpyHostToDevice, c->stream));
     }
@@ -377,7 +388,7 @@ int32_t rtz_scene_upload(rtz_context* c, const rtz_sphere* sp, uint64_t n) {
     RTZ_CUDA(cudaMemcpyAsync(c->dspheres.p, ds.data(), ds.size() * sizeof(rtz::DSphere), cudaMemcpyHostToDevice,
                              c->stream));
     RTZ_CUDA(cudaStreamSynchronize(c->stream));  // the staging vectors die here
-    c->h_geom = g;  // host copy: small scenes travel to the kernel as a __grid_constant__ parameter
+    c->h_pairs = pr;  // host copy: small scenes can travel to the kernel as a __grid_constant__ parameter
     c->n_spheres = (int)n, c->n_pad = n_pad;
     return RTZ_OK;
 }
@@ -486,7 +497,7 @@ int32_t rtz_probe_hit(const rtz_sphere* sp, uint64_t n, const double o[3], const
     if (rc != RTZ_OK) return rc;
     rtz::ProbeHitOut* dout;
     RTZ_CUDA(cudaMalloc(&dout, sizeof(*dout)));
-    rtz::probe_hit_kernel<<<1, 1, 0, sc.c->stream>>>(sc.c->geom.p, sc.c->nr2.p, sc.c->aux.p, sc.c->n_pad, (float)o[0], (float)o[1],
+    rtz::probe_hit_kernel<<<1, 1, 0, sc.c->stream>>>(sc.c->geom.p, sc.c->pairs.p, sc.c->aux.p, sc.c->n_pad, (float)o[0], (float)o[1],
                                                     (float)o[2], (float)d[0], (float)d[1], (float)d[2], (float)tmin,
                                                     (float)tmax, dout);
     rtz::ProbeHitOut h;
@@ -518,7 +529,7 @@ int32_t rtz_probe_scatter(const rtz_sphere* sp, uint64_t n, int32_t index, const
     const rtz::DevCamera dc = to_dev_camera(cam, seed);
     rtz::ProbeScatterOut* dout;
     RTZ_CUDA(cudaMalloc(&dout, sizeof(*dout)));
-    rtz::probe_scatter_kernel<<<1, 1, 0, sc.c->stream>>>(dc, sc.c->geom.p, sc.c->nr2.p, sc.c->aux.p, sc.c->albedo.p, index,
+    rtz::probe_scatter_kernel<<<1, 1, 0, sc.c->stream>>>(dc, sc.c->geom.p, sc.c->pairs.p, sc.c->aux.p, sc.c->albedo.p, index,
                                                         (float)o[0], (float)o[1], (float)o[2], (float)d[0], (float)d[1],
                                                         (float)d[2], pixel, sample, bounce, dout);
     rtz::ProbeScatterOut h;
@@ -575,7 +586,7 @@ int32_t rtz_probe_uniform(uint64_t seed, uint32_t pixel, uint32_t sample, uint32
 }
 
 int32_t rtz_measure_fp32_peak(int32_t device, int32_t variant, double* tflops_out) {
-    if (!tflops_out || variant < 0 || variant > 1) return RTZ_ERR_BAD_ARG;
+    if (!tflops_out || variant < 0 || variant > 2) return RTZ_ERR_BAD_ARG;
     ScopedCtx sc;
     int32_t rc = rtz_context_create(device, nullptr, &sc.c);
     if (rc != RTZ_OK) return rc;
@@ -589,8 +600,10 @@ int32_t rtz_measure_fp32_peak(int32_t device, int32_t variant, double* tflops_ou
         cudaEventRecord(c->ev[0], c->stream);
         if (variant == 0)
             rtz::ffma_peak_kernel<0><<<blocks, threads, 0, c->stream>>>(1.0000001f, 1e-7f, iters, sink);
-        else
+        else if (variant == 1)
             rtz::ffma_peak_kernel<1><<<blocks, threads, 0, c->stream>>>(1.0000001f, 1e-7f, iters, sink);
+        else if (variant == 2)
+            rtz::ffma_peak_kernel<2><<<blocks, threads, 0, c->stream>>>(1.0000001f, 1e-7f, iters, sink);
         cudaEventRecord(c->ev[1], c->stream);
         e = cudaStreamSynchronize(c->stream);
         float ms = 0;
@@ -599,7 +612,7 @@ int32_t rtz_measure_fp32_peak(int32_t device, int32_t variant, double* tflops_ou
     }
     cudaFree(sink);
     RTZ_CUDA(e);
-    const double flops = 2.0 * 16 * (double)iters * (double)blocks * threads;
+    double flops = 2.0 * 16 * (double)iters * (double)blocks * threads;
     *tflops_out = flops / (best_ms * 1e-3) / 1e12;
     return RTZ_OK;
 }

@@ -180,14 +180,13 @@ __device__ __forceinline__ RayK ray_constants(const Path& p) {
     k.tx = 2.0f * p.ox, k.ty = 2.0f * p.oy, k.tz = 2.0f * p.oz;
     return k;
 }
-// candidate test: sign of the expanded discriminant.  geo[i] = {cx, cy, cz, -(|c|^2 - r^2)}
-__device__ __forceinline__ float expanded_disc(const float4 g, const Path& p, const RayK& k) {
-    const float h = fmaf(p.dz, g.z, fmaf(p.dy, g.y, fmaf(p.dx, g.x, k.k1)));
-    const float e = g.w + k.nk2;
-    const float w = fmaf(k.tz, g.z, fmaf(k.ty, g.y, fmaf(k.tx, g.x, e)));
+// candidate test: sign of the expanded discriminant; cw = -(|c|^2 - r^2) from the host
+__device__ __forceinline__ float expanded_disc(float cx, float cy, float cz, float cw, const Path& p, const RayK& k) {
+    const float h = fmaf(p.dz, cz, fmaf(p.dy, cy, fmaf(p.dx, cx, k.k1)));
+    const float w = fmaf(k.tz, cz, fmaf(k.ty, cy, fmaf(k.tx, cx, k.nk2))) + cw;
     return fmaf(h, h, w);
 }
-// root of a candidate from the direct form (src/sphere.zig:27-42); nr2[i] = -r^2
+// root of a candidate from the direct form (src/sphere.zig:27-42); g = {cx, cy, cz, -r^2}
 __device__ __forceinline__ void candidate_root(const float4 g, float nr2, int i, const Path& p, float& closest,
                                                int& best) {
     const float ocx = g.x - p.ox, ocy = g.y - p.oy, ocz = g.z - p.oz;
@@ -197,17 +196,21 @@ __device__ __forceinline__ void candidate_root(const float4 g, float nr2, int i,
     if (disc >= 0.0f) slow_path(h, disc, i, p.self, p.tmin_d, closest, best);
 }
 
-// scalar sweep: serves the one-ray probes; the render kernel runs the same arithmetic two rays
-// at a time (sweep2 in rtz_kernels.cuh)
-__device__ __forceinline__ void sweep(const float4* __restrict__ geo, const float* __restrict__ nr2, int n,
-                                      const Path& p, float& t_out, int& best_out) {
+// scalar sweep over plain rows {cx, cy, cz, -r^2} + the pair layout's w: serves the one-ray probes;
+// the render kernel runs the same arithmetic on sphere pairs (sweep2 in rtz_kernels.cuh)
+__device__ __forceinline__ float pair_w(const float4* __restrict__ pairs, int i) {
+    const float4 p1 = pairs[(i & ~1) + 1];
+    return (i & 1) ? p1.w : p1.z;
+}
+__device__ __forceinline__ void sweep_rows(const float4* __restrict__ geo, const float4* __restrict__ pairs, int first,
+                                           int n, const Path& p, float& t_out, int& best_out) {
     float closest = __int_as_float(0x7f800000);  // +inf
     int best = -1;
     const RayK k = ray_constants(p);
-    for (int i = 0; i < n; ++i) {
+    for (int i = first; i < first + n; ++i) {
         const float4 g = geo[i];
-        const float d = expanded_disc(g, p, k);
-        if (!(__float_as_uint(d) >> 31)) candidate_root(g, nr2[i], i, p, closest, best);
+        const float d = expanded_disc(g.x, g.y, g.z, pair_w(pairs, i), p, k);
+        if (!(__float_as_uint(d) >> 31)) candidate_root(g, g.w, i, p, closest, best);
     }
     t_out = closest;
     best_out = best;

@@ -19,8 +19,9 @@ struct ShardGeom {
 struct TraceParams {
     DevCamera cam;
     ShardGeom sh;
-    const float4* geom;     // [n_pad+1] {cx, cy, cz, -(|c|^2 - r^2)}
-    const float* nr2;       // [n_pad]   -r^2 (root of a candidate, direct form)
+    const float4* pairs;    // [n_pad]   sweep layout, spheres in pairs (A=2p, B=2p+1):
+                            //           [2p] = {cxA,cxB,cyA,cyB}  [2p+1] = {czA,czB,wA,wB},  w = -(|c|^2 - r^2)
+    const float4* geom;     // [n_pad]   per-lane lookups: {cx, cy, cz, -r^2}
     const float4* aux;      // [n_pad] {r, 1/r, fuzz|ior, type}
     const float4* albedo;   // [n_pad] {r,g,b,1/ior}
     int n_spheres;
@@ -39,7 +40,7 @@ struct TraceParams {
 constexpr int kMaxConstSpheres = 1920;  // 30 KiB of the 32 KiB parameter space
 struct TraceParamsConst {
     TraceParams p;
-    float4 geo[kMaxConstSpheres];
+    float4 pairs[kMaxConstSpheres];
 };
 
 // local (compact, padded) pixel index -> global pixel; false for tile padding
@@ -109,59 +110,67 @@ struct Slot {
     bool alive;
 };
 
+
 // evaluate the candidates of one 32-sphere block for one path: Sphere.hit's root selection
 // (src/sphere.zig:35-42) with the shrinking t_max of HittableList.hit (src/hittable.zig:66-73).
-// `gather`/`nr2` are the copies of the geometry used for per-lane (divergent) lookups.
-__device__ __forceinline__ void resolve_candidates(const float4* __restrict__ gather, const float* __restrict__ nr2,
-                                                   unsigned cand, int base, int cnt, const Path& p, float& closest,
-                                                   int& best) {
+// `gather[i]` = {cx, cy, cz, -r^2} serves the per-lane (divergent) lookups.
+__device__ __forceinline__ void resolve_candidates(const float4* __restrict__ gather, unsigned cand, int base, int cnt,
+                                                   const Path& p, float& closest, int& best) {
     while (cand) {
         const int bit = 31 - __clz(cand);  // highest bit = lowest sphere index: ascending order
         cand &= ~(1u << bit);
         const int i = base + (cnt - 1 - bit);
-        candidate_root(gather[i], nr2[i], i, p, closest, best);
+        const float4 g = gather[i];
+        candidate_root(g, g.w, i, p, closest, best);
     }
 }
 
-// HittableList.hit for the two paths of a thread.  geo[i] = {cx, cy, cz, -(|c|^2-r^2)}; every
-// value is a scalar-broadcast operand of the packed instruction (R.F32 / UR.F32).  n_pad is a
-// multiple of 8 (padding spheres have .w = -inf -> disc = -inf).  `geo` is warp-uniform storage:
-// shared memory (LDS.128) or the constant bank; `gather`/`nr2` serve the per-lane lookups.
-// Per sphere and thread: 1 LDS.128 + 7 FFMA2 + 1 FADD2 + 2 SHF for TWO ray-sphere tests.
-__device__ __forceinline__ void sweep2(const float4* __restrict__ geo, const float4* __restrict__ gather,
-                                       const float* __restrict__ nr2, int n_pad, const Path& a, const Path& b,
-                                       float& ta, int& ia, float& tb, int& ib) {
+// One path against one PAIR of spheres: 7 FFMA2 + 1 FADD2 = two ray-sphere tests (17 algorithmic
+// FLOP each).  The ray constants are scalar-broadcast operands (R.F32), the sphere pair is the
+// packed operand; this orientation needs fewer register-file reads per FFMA2 than packing two rays
+// (tools/ubench/sweep_shapes.cu), and on sm_100 the register file, not the FMA pipe, is what bounds
+// a packed instruction with several distinct register operands (tools/ubench/ffma2_patterns.cu).
+__device__ __forceinline__ void test_pair(const float4 p0, const float4 p1, const Path& p, const RayK& k,
+                                          unsigned& mask) {
+    const float2 cx = make_float2(p0.x, p0.y), cy = make_float2(p0.z, p0.w);
+    const float2 cz = make_float2(p1.x, p1.y), cw = make_float2(p1.z, p1.w);
+    float2 h = __ffma2_rn(make_float2(p.dx, p.dx), cx, make_float2(k.k1, k.k1));
+    h = __ffma2_rn(make_float2(p.dy, p.dy), cy, h);
+    h = __ffma2_rn(make_float2(p.dz, p.dz), cz, h);
+    float2 w = __ffma2_rn(make_float2(k.tx, k.tx), cx, make_float2(k.nk2, k.nk2));
+    w = __ffma2_rn(make_float2(k.ty, k.ty), cy, w);
+    w = __ffma2_rn(make_float2(k.tz, k.tz), cz, w);
+    w = __fadd2_rn(w, cw);
+    const float2 disc = __ffma2_rn(h, h, w);
+    mask = __funnelshift_l(__float_as_uint(disc.x), mask, 1);  // append sign(disc): sphere 2p ...
+    mask = __funnelshift_l(__float_as_uint(disc.y), mask, 1);  // ... then sphere 2p+1
+}
+
+// HittableList.hit for the two paths of a thread.  `pairs` is warp-uniform storage (shared memory
+// or the constant bank): per sphere pair 2 LDS.128 + 2 x (7 FFMA2 + 1 FADD2 + 2 SHF) for FOUR tests.
+// n_pad is a multiple of 8; padding spheres have w = -inf -> disc = -inf -> never a candidate.
+__device__ __forceinline__ void sweep2(const float4* __restrict__ pairs, const float4* __restrict__ gather, int n_pad,
+                                       const Path& a, const Path& b, float& ta, int& ia, float& tb, int& ib) {
     const RayK ka = ray_constants(a), kb = ray_constants(b);
-    const float2 dx = make_float2(a.dx, b.dx), dy = make_float2(a.dy, b.dy), dz = make_float2(a.dz, b.dz);
-    const float2 k1 = make_float2(ka.k1, kb.k1), nk2 = make_float2(ka.nk2, kb.nk2);
-    const float2 tx = make_float2(ka.tx, kb.tx), ty = make_float2(ka.ty, kb.ty), tz = make_float2(ka.tz, kb.tz);
     float ca = __int_as_float(0x7f800000), cb = ca;
     int ba = -1, bb = -1;
     for (int base = 0; base < n_pad; base += 32) {
         const int cnt = min(32, n_pad - base);
         unsigned ma = 0xFFFFFFFFu, mb = 0xFFFFFFFFu;  // 1 = miss
-        const float4* g = geo + base;
+        const float4* g = pairs + base;
 #pragma unroll 1
         for (int k = 0; k < cnt; k += 8) {
 #pragma unroll
-            for (int u = 0; u < 8; ++u) {
-                const float4 s = g[k + u];
-                float2 h = __ffma2_rn(dx, make_float2(s.x, s.x), k1);
-                h = __ffma2_rn(dy, make_float2(s.y, s.y), h);
-                h = __ffma2_rn(dz, make_float2(s.z, s.z), h);
-                float2 w = __fadd2_rn(make_float2(s.w, s.w), nk2);
-                w = __ffma2_rn(tx, make_float2(s.x, s.x), w);
-                w = __ffma2_rn(ty, make_float2(s.y, s.y), w);
-                w = __ffma2_rn(tz, make_float2(s.z, s.z), w);
-                const float2 disc = __ffma2_rn(h, h, w);
-                ma = __funnelshift_l(__float_as_uint(disc.x), ma, 1);  // append sign(disc)
-                mb = __funnelshift_l(__float_as_uint(disc.y), mb, 1);
+            for (int u = 0; u < 8; u += 2) {
+                const float4 p0 = g[k + u], p1 = g[k + u + 1];
+                test_pair(p0, p1, a, ka, ma);
+                test_pair(p0, p1, b, kb, mb);
             }
         }
         const unsigned canda = ~ma, candb = ~mb;
         if (canda | candb) {
-            resolve_candidates(gather, nr2, canda, base, cnt, a, ca, ba);
-            resolve_candidates(gather, nr2, candb, base, cnt, b, cb, bb);
+            resolve_candidates(gather, canda, base, cnt, a, ca, ba);
+            resolve_candidates(gather, candb, base, cnt, b, cb, bb);
         }
     }
     ta = ca, ia = ba, tb = cb, ib = bb;
@@ -188,8 +197,8 @@ __device__ __forceinline__ void finish_or_continue(const TraceParams& P, const f
 
 // The body shared by the two kernels below.  `geo` is the warp-uniform geometry the sweep reads,
 // `gather` the copy for per-lane lookups (candidate roots, hit records).
-__device__ __forceinline__ void trace_body(const TraceParams& P, const float4* __restrict__ geo,
-                                           const float4* __restrict__ gather, const float* __restrict__ nr2) {
+__device__ __forceinline__ void trace_body(const TraceParams& P, const float4* __restrict__ pairs,
+                                           const float4* __restrict__ gather) {
     // material rows are touched once per HIT (not per test): they stay in global memory / L1
     const float4* s_aux = P.aux;
     const float4* s_alb = P.albedo;
@@ -221,13 +230,16 @@ __device__ __forceinline__ void trace_body(const TraceParams& P, const float4* _
                     unsigned long long cid = 0;
                     if (lane == 0) cid = atomicAdd(P.counter, 1ULL);
                     cid = __shfl_sync(0xFFFFFFFFu, cid, 0);
-                    if (cid >= P.n_chunks) {
+                    // the conditions below are the same in every lane; voting on them makes that
+                    // visible to ptxas (uniform branches keep the warp provably converged)
+                    if (__any_sync(0xFFFFFFFFu, cid >= P.n_chunks)) {
                         exhausted = true;
                         break;
                     }
                     ch_lp = (uint32_t)(cid / P.chunks_per_pixel);
                     const uint32_t part = (uint32_t)(cid - (unsigned long long)ch_lp * P.chunks_per_pixel);
-                    if (!local_to_global(P.sh, cam.width, cam.height, ch_lp, ch_x, ch_y)) continue;  // tile padding
+                    const bool inside = local_to_global(P.sh, cam.width, cam.height, ch_lp, ch_x, ch_y);
+                    if (__any_sync(0xFFFFFFFFu, !inside)) continue;  // tile padding
                     ch_next = part * P.chunk;
                     ch_end = min(ch_next + P.chunk, cam.spp);
                 }
@@ -251,11 +263,13 @@ __device__ __forceinline__ void trace_body(const TraceParams& P, const float4* _
                 need_a = __ballot_sync(0xFFFFFFFFu, !A.alive);
                 need_b = __ballot_sync(0xFFFFFFFFu, !B.alive);
             }
-            if ((need_a & need_b) == 0xFFFFFFFFu) break;  // queue drained and every path finished
         }
+        // loop exit on a FRESH warp vote: the condition is warp-uniform by construction, which lets
+        // ptxas keep the sweep below on the uniform datapath (uniform loads / UR operands)
+        if (__ballot_sync(0xFFFFFFFFu, A.alive || B.alive) == 0u) break;  // queue drained, every path finished
         float ta, tb;
         int ia, ib;
-        sweep2(geo, gather, nr2, P.n_pad, A.path, B.path, ta, ia, tb, ib);
+        sweep2(pairs, gather, P.n_pad, A.path, B.path, ta, ia, tb, ib);
         if (A.alive) finish_or_continue(P, gather, s_aux, s_alb, A, ta, ia, n_seg, n_samp, n_cap, n_abs);
         if (B.alive) finish_or_continue(P, gather, s_aux, s_alb, B, tb, ib, n_seg, n_samp, n_cap, n_abs);
     }
@@ -279,16 +293,16 @@ __device__ __forceinline__ void trace_body(const TraceParams& P, const float4* _
 // K1a: geometry in the constant bank (kernel parameter).  No shared memory at all.
 template <int kBlock>
 __global__ void __launch_bounds__(kBlock) trace_kernel_const(const __grid_constant__ TraceParamsConst C) {
-    trace_body(C.p, C.geo, C.p.geom, C.p.nr2);
+    trace_body(C.p, C.pairs, C.p.geom);
 }
 
 // K1b: geometry staged into shared memory by one 1-D TMA bulk copy (cp.async.bulk + mbarrier);
-// for scenes too large for the parameter space (up to ~14 500 spheres in 227 KiB).
-template <int kBlock>
-__global__ void __launch_bounds__(kBlock) trace_kernel_smem(const __grid_constant__ TraceParams P) {
+// the default; 32 B of shared memory per sphere (up to ~7 200 spheres in 227 KiB).
+template <int kBlock, int kMinBlocks>
+__global__ void __launch_bounds__(kBlock, kMinBlocks) trace_kernel_smem(const __grid_constant__ TraceParams P) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    float4* s_geo = reinterpret_cast<float4*>(smem_raw);               // [n_pad + 1]
-    float* s_nr2 = reinterpret_cast<float*>(s_geo + P.n_pad + 1);       // [n_pad]
+    float4* s_pairs = reinterpret_cast<float4*>(smem_raw);  // [n_pad] sweep layout
+    float4* s_geom = s_pairs + P.n_pad;                      // [n_pad] per-lane lookups
     __shared__ __align__(8) uint64_t s_bar;
     if (threadIdx.x == 0) {
         mbar_init(&s_bar, 1);
@@ -296,13 +310,13 @@ __global__ void __launch_bounds__(kBlock) trace_kernel_smem(const __grid_constan
     }
     __syncthreads();
     if (threadIdx.x == 0) {
-        const uint32_t bytes = (uint32_t)(P.n_pad + 1) * 16u, bytes2 = (uint32_t)P.n_pad * 4u;
-        mbar_expect_tx(&s_bar, bytes + bytes2);
-        bulk_g2s(s_geo, P.geom, bytes, &s_bar);
-        bulk_g2s(s_nr2, P.nr2, bytes2, &s_bar);
+        const uint32_t bytes = (uint32_t)P.n_pad * 16u;
+        mbar_expect_tx(&s_bar, 2u * bytes);
+        bulk_g2s(s_pairs, P.pairs, bytes, &s_bar);
+        bulk_g2s(s_geom, P.geom, bytes, &s_bar);
     }
     mbar_wait(&s_bar, 0);
-    trace_body(P, s_geo, s_geo, s_nr2);
+    trace_body(P, s_pairs, s_geom);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -423,7 +437,7 @@ struct ProbeHitOut {
     float t, len;
     float p[3], n[3];
 };
-__global__ void probe_hit_kernel(const float4* geom, const float* nr2, const float4* aux, int n_pad, float ox, float oy, float oz,
+__global__ void probe_hit_kernel(const float4* geom, const float4* pairs, const float4* aux, int n_pad, float ox, float oy, float oz,
                                  float dx, float dy, float dz, float tmin, float tmax, ProbeHitOut* out) {
     Path p;
     p.ox = ox, p.oy = oy, p.oz = oz, p.self = -1, p.bounce = 0, p.tr = p.tg = p.tb = 1.f;
@@ -431,7 +445,7 @@ __global__ void probe_hit_kernel(const float4* geom, const float* nr2, const flo
     const float len = sqrtf(fmaf(dz, dz, fmaf(dy, dy, dx * dx)));
     float t;
     int best;
-    sweep(geom, nr2, n_pad, p, t, best);
+    sweep_rows(geom, pairs, 0, n_pad, p, t, best);
     // the render kernel's t_max is +inf; a finite t_max (unit tests) is applied here
     if (best >= 0 && !(t < tmax * len)) best = -1;
     out->hit = best >= 0, out->index = best, out->len = len, out->t = t;
@@ -449,7 +463,7 @@ struct ProbeScatterOut {
     int scattered, term;
     float o[3], d[3], att[3], len;
 };
-__global__ void probe_scatter_kernel(DevCamera cam, const float4* geom, const float* nr2, const float4* aux,
+__global__ void probe_scatter_kernel(DevCamera cam, const float4* geom, const float4* pairs, const float4* aux,
                                      const float4* albedo,
                                      int index, float ox, float oy, float oz, float dx, float dy, float dz,
                                      uint32_t pixel, uint32_t sample, uint32_t bounce, ProbeScatterOut* out) {
@@ -458,13 +472,13 @@ __global__ void probe_scatter_kernel(DevCamera cam, const float4* geom, const fl
     set_direction(p, dx, dy, dz, cam.tmin);
     float t;
     int best;
-    sweep(geom + index, nr2 + index, 1, p, t, best);  // Sphere.hit on that one sphere
+    sweep_rows(geom, pairs, index, 1, p, t, best);  // Sphere.hit on that one sphere
     out->scattered = 0, out->term = -1;
     if (best < 0) return;
     RngKey k{cam.key0, cam.key1, pixel, sample};
     float sr, sg, sb;
     int term = -1;
-    const bool done = shade(cam, k, geom + index, aux + index, albedo + index, p, t, 0, sr, sg, sb, term);
+    const bool done = shade(cam, k, geom, aux, albedo, p, t, index, sr, sg, sb, term);
     out->term = term;
     if (done) return;
     out->scattered = 1;
@@ -497,12 +511,12 @@ __global__ void __launch_bounds__(256) ffma_peak_kernel(float a, float b, int it
     float x[C];
 #pragma unroll
     for (int i = 0; i < C; ++i) x[i] = (float)(threadIdx.x + i) * 1e-3f;
-    if (kVariant == 0) {
+    if (kVariant == 0) {  // scalar FFMA, 16 independent chains
         for (int it = 0; it < iters; ++it) {
 #pragma unroll
             for (int i = 0; i < C; ++i) x[i] = fmaf(x[i], a, b);
         }
-    } else {
+    } else if (kVariant == 1) {  // packed FFMA2, all operands packed
         float2 aa = make_float2(a, a), bb = make_float2(b, b);
         for (int it = 0; it < iters; ++it) {
 #pragma unroll
@@ -510,6 +524,17 @@ __global__ void __launch_bounds__(256) ffma_peak_kernel(float a, float b, int it
                 float2 v = __ffma2_rn(make_float2(x[i], x[i + 1]), aa, bb);
                 x[i] = v.x, x[i + 1] = v.y;
             }
+        }
+    } else {  // packed FFMA2 with one scalar-broadcast operand (R.F32), as the sweep uses it
+        float2 bb = make_float2(b, b);
+        float s = a;
+        for (int it = 0; it < iters; ++it) {
+#pragma unroll
+            for (int i = 0; i < C; i += 2) {
+                float2 v = __ffma2_rn(make_float2(x[i], x[i + 1]), make_float2(s, s), bb);
+                x[i] = v.x, x[i + 1] = v.y;
+            }
+            s = __int_as_float(__float_as_int(s) ^ (it & 1));  // keep the scalar in a vector register
         }
     }
     float s = 0.f;

@@ -225,13 +225,13 @@ def test_sphere_count_limits(pkg, gpu, orc):
     mrgb, _, mst = _mirror(orc, cam, buf, 4096, 5)
     assert st.sphere_tests == st.segments * 4096 and st.segments == mst.segments
     assert np.array_equal(img.cpu().numpy().reshape(-1, 3), mrgb)
-    # 20 B per sphere: 11 000 spheres still fit the 227 KiB of one SM ...
+    # 32 B per sphere: 7 000 spheres still fit the 227 KiB of one SM ...
     big = (R.Sphere * 16384)()
     for i in range(16384):
         big[i] = buf[i % 4096]
-    gpu.upload(big, 11000)
+    gpu.upload(big, 7000)
     img2, st2 = gpu.render(cam)
-    assert st2.sphere_tests == st2.segments * 11000
+    assert st2.sphere_tests == st2.segments * 7000
     # ... 16 384 cannot be staged: explicit error, no fallback
     gpu.upload(big, 16384)
     with pytest.raises(pkg.RtzError) as e:
