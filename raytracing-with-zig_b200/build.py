@@ -75,8 +75,15 @@ def build_host(force: bool = False) -> Path:
 
 
 def build_all(force: bool = False, verbose: bool = False) -> None:
-    build_librtz(force, verbose)
-    build_host(force)
+    """Build everything; serialised with a file lock so that N torchrun ranks can all call it."""
+    import fcntl
+    with open(PKG / ".build.lock", "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            build_librtz(force, verbose)
+            build_host(force)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
 
 
 if __name__ == "__main__":

@@ -186,11 +186,24 @@ int32_t render_path(rtz_context* ctx, const rtz_camera* cam, const rtz::ShardGeo
         std::memcpy(C.pairs, ctx->h_pairs.data(), (size_t)ctx->n_pad * sizeof(float4));
         rc = launch_trace(ctx, rtz::trace_kernel_const<256>, C, P.n_chunks, 256, 0);
     } else {
-        switch (ctx->variant) {  // RTZ_VARIANT: launch-shape experiments; 0 = the measured best
+        // Launch shape: the one that keeps most warps resident for this scene's shared-memory
+        // footprint.  <128,5> (94 registers, 20 warps/SM) is the measured best while five CTAs fit;
+        // large scenes trade CTAs for wider CTAs.  RTZ_VARIANT=1..3 forces a shape (experiments).
+        int occ[3] = {0, 0, 0};
+        RTZ_CUDA(cudaFuncSetAttribute(rtz::trace_kernel_smem<128, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        RTZ_CUDA(cudaFuncSetAttribute(rtz::trace_kernel_smem<256, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        RTZ_CUDA(cudaFuncSetAttribute(rtz::trace_kernel_smem<512, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        RTZ_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ[0], rtz::trace_kernel_smem<128, 5>, 128, smem));
+        RTZ_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ[1], rtz::trace_kernel_smem<256, 2>, 256, smem));
+        RTZ_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ[2], rtz::trace_kernel_smem<512, 1>, 512, smem));
+        const int warps[3] = {occ[0] * 4, occ[1] * 8, occ[2] * 16};
+        int shape = 0;
+        for (int k = 1; k < 3; ++k)
+            if (warps[k] > warps[shape]) shape = k;
+        if (ctx->variant >= 1 && ctx->variant <= 3) shape = ctx->variant - 1;
+        switch (shape) {
             case 1: rc = launch_trace(ctx, rtz::trace_kernel_smem<256, 2>, P, P.n_chunks, 256, smem); break;
-            case 2: rc = launch_trace(ctx, rtz::trace_kernel_smem<256, 3>, P, P.n_chunks, 256, smem); break;
-            case 3: rc = launch_trace(ctx, rtz::trace_kernel_smem<128, 4>, P, P.n_chunks, 128, smem); break;
-            case 4: rc = launch_trace(ctx, rtz::trace_kernel_smem<128, 6>, P, P.n_chunks, 128, smem); break;
+            case 2: rc = launch_trace(ctx, rtz::trace_kernel_smem<512, 1>, P, P.n_chunks, 512, smem); break;
             default: rc = launch_trace(ctx, rtz::trace_kernel_smem<128, 5>, P, P.n_chunks, 128, smem); break;
         }
     }

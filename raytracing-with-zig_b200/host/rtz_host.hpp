@@ -429,14 +429,44 @@ struct Scene {
     }
     void deinit() { world.deinit(); }
 
-    void generateWorld() {  // :48-134 — draw order per grid cell is part of the contract (Q15)
+    void generateWorld() { generateGrid(0, 22, 11); }  // :48-134: a, b in 0..22, offsets a-11, b-11
+
+    // BASELINE config 5: generateWorld generalised to a G x G grid centred on the
+    // origin, G = ceil(sqrt(n-4)) (grown until enough cells survive the (4,.2,0) exclusion), then cut
+    // to exactly n spheres: ground, the three big spheres, then the small ones in generation order.
+    // Not part of the reference; it exists so the sphere-count sweep needs no other scene source.
+    bool generateSweep(size_t n) {
+        if (n < 4) return false;
+        int G = (int)std::ceil(std::sqrt((double)(n - 4)));
+        if (G < 1) G = 1;
+        const DefaultPrng start = *prng;
+        for (int grow = 0; grow < 64; ++grow) {
+            *prng = start;  // every attempt replays the same stream
+            world.clear();
+            const int lo = -(G / 2) - grow, hi = -(G / 2) + G + grow;
+            generateGrid(lo, hi, 0);
+            const size_t total = world.objects.size();
+            if (total >= n) {
+                std::vector<Hittable> cut;
+                cut.push_back(world.objects[0]);
+                for (size_t k = total - 3; k < total; ++k) cut.push_back(world.objects[k]);
+                for (size_t k = 1; cut.size() < n; ++k) cut.push_back(world.objects[k]);
+                world.objects = cut;
+                return true;
+            }
+        }
+        return false;
+    }
+
+    // the body of generateWorld for cells a, b in [lo, hi) with centre offsets (a - shift, b - shift)
+    void generateGrid(int lo, int hi, int shift) {  // draw order per grid cell is part of the contract (Q15)
         DefaultPrng* g = prng.get();
         world.add(Hittable::init(HittableType::sphere,
                                  {{0, -1000, 0}, 1000, Material::init(MaterialType::lambertian, {{0.5, 0.5, 0.5}, 0, g, 1.0})}));
-        for (int a = 0; a < 22; ++a) {
-            const double xOffset = (double)a - 11;
-            for (int b = 0; b < 22; ++b) {
-                const double zOffset = (double)b - 11;
+        for (int a = lo; a < hi; ++a) {
+            const double xOffset = (double)a - shift;
+            for (int b = lo; b < hi; ++b) {
+                const double zOffset = (double)b - shift;
                 const double chooseMat = util::randomDouble(g);
                 const double cx = xOffset + 0.9 * util::randomDouble(g);
                 const double cz = zOffset + 0.9 * util::randomDouble(g);

@@ -16,6 +16,15 @@ uint64_t rtzh_scene_generate_world(uint64_t seed, int32_t has_seed, rtz_sphere* 
     return f.size();
 }
 
+// BASELINE config 5: exactly n spheres of the generalised final scene (0 on failure).
+uint64_t rtzh_scene_generate_sweep(uint64_t seed, uint64_t n, rtz_sphere* out) {
+    Scene s = Scene::init(seed);
+    if (!s.generateSweep(n)) return 0;
+    const auto f = s.world.flat();
+    for (uint64_t i = 0; i < f.size(); ++i) out[i] = f[i];
+    return f.size();
+}
+
 uint64_t rtzh_scene_generate_chapter13(rtz_sphere* out, uint64_t cap) {
     Scene s = Scene::init(0);
     s.generateChapter13();

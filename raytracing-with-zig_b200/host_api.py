@@ -22,6 +22,8 @@ def hostlib() -> C.CDLL:
         u64, i32, f64 = C.c_uint64, C.c_int32, C.c_double
         l.rtzh_scene_generate_world.restype = u64
         l.rtzh_scene_generate_world.argtypes = [u64, i32, C.POINTER(B.rtz_sphere), u64]
+        l.rtzh_scene_generate_sweep.restype = u64
+        l.rtzh_scene_generate_sweep.argtypes = [u64, u64, C.POINTER(B.rtz_sphere)]
         l.rtzh_scene_generate_chapter13.restype = u64
         l.rtzh_scene_generate_chapter13.argtypes = [C.POINTER(B.rtz_sphere), u64]
         l.rtzh_camera_build.restype = i32
@@ -40,6 +42,15 @@ def generate_world(seed: int | None):
     buf = (B.rtz_sphere * 512)()
     n = hostlib().rtzh_scene_generate_world(seed or 0, 0 if seed is None else 1, buf, 512)
     return buf, int(n)
+
+
+def generate_sweep(seed: int, n: int):
+    """BASELINE config 5: the final scene generalised to exactly n spheres (16 ... 4096)."""
+    buf = (B.rtz_sphere * n)()
+    got = hostlib().rtzh_scene_generate_sweep(seed, n, buf)
+    if got != n:
+        raise ValueError(f"cannot build a {n}-sphere scene")
+    return buf, n
 
 
 def generate_chapter13():

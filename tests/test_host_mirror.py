@@ -26,6 +26,17 @@ def test_generate_world_bit_identical_to_oracle(host, orc, seed):
     assert bytes(buf)[: n * C.sizeof(R.Sphere)] == bytes(obuf)[: n * C.sizeof(R.Sphere)]
 
 
+@pytest.mark.parametrize("n", [16, 32, 64, 128, 256, 512, 1024, 2048, 4096])
+def test_generate_sweep_identical_to_oracle(host, orc, n):
+    """BASELINE config 5 scenes: product host generator == oracle generator, byte for byte."""
+    buf, got = host.generate_sweep(0xDEADBEEF, n)
+    prng = orc.orc_prng_new(0xDEADBEEF)
+    obuf = (R.Sphere * n)()
+    assert orc.orc_generate_sweep(prng, n, obuf) == n == got
+    assert bytes(buf) == bytes(obuf)
+    assert buf[0].radius == 1000 and [buf[i].radius for i in (1, 2, 3)] == [1, 1, 1]
+
+
 def test_generate_chapter13_identical(host, orc):
     buf, n = host.generate_chapter13()
     obuf, on = R.chapter13_scene()
