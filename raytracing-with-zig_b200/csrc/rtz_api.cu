@@ -74,7 +74,8 @@ struct rtz_context {
     int sm_count = 0;
     size_t smem_optin = 0;
     int variant = 0;
-    bool geo_const = false;  // RTZ_GEO_CONST=1: experimental constant-bank geometry kernel (default: TMA + shared memory)
+    bool geo_const = true;   // scenes that fit the kernel-parameter space use the constant-bank kernel;
+                             // RTZ_GEO_CONST=0 forces the TMA + shared-memory kernel
     // scene (device SoA f32 + the f64 copy the legacy kernel reads)
     DevBuf<float4> geom, pairs, aux, albedo;
     DevBuf<rtz::DSphere> dspheres;
@@ -181,10 +182,16 @@ int32_t render_path(rtz_context* ctx, const rtz_camera* cam, const rtz::ShardGeo
     RTZ_CUDA(cudaEventRecord(ctx->ev[1], ctx->stream));
     int32_t rc;
     if (use_const) {
-        static thread_local rtz::TraceParamsConst C;  // 30 KiB: keep it off the stack
+        static thread_local rtz::TraceParamsConst C;  // 8 KiB: keep it off the stack
         C.p = P;
         std::memcpy(C.pairs, ctx->h_pairs.data(), (size_t)ctx->n_pad * sizeof(float4));
-        rc = launch_trace(ctx, rtz::trace_kernel_const<256>, C, P.n_chunks, 256, 0);
+        // <128,6> (80 registers, 24 warps/SM) is the measured best; the uniform loads want occupancy
+        if (ctx->variant == 1)
+            rc = launch_trace(ctx, rtz::trace_kernel_const<256, 3>, C, P.n_chunks, 256, 0);
+        else if (ctx->variant == 2)
+            rc = launch_trace(ctx, rtz::trace_kernel_const<128, 5>, C, P.n_chunks, 128, 0);
+        else
+            rc = launch_trace(ctx, rtz::trace_kernel_const<128, 6>, C, P.n_chunks, 128, 0);
     } else {
         // Launch shape: the one that keeps most warps resident for this scene's shared-memory
         // footprint.  <128,5> (94 registers, 20 warps/SM) is the measured best while five CTAs fit;

@@ -37,7 +37,7 @@ struct TraceParams {
 // Scenes of up to kMaxConstSpheres spheres travel as a __grid_constant__ kernel parameter: the
 // sweep then reads them through the constant bank with uniform loads (LDCU -> uniform registers
 // -> UR operands of FADD2/FFMA2), which needs no LDS, no vector registers and no shared memory.
-constexpr int kMaxConstSpheres = 1920;  // 30 KiB of the 32 KiB parameter space
+constexpr int kMaxConstSpheres = 512;  // 8 KiB: what the constant cache serves at full rate (1024 spheres already thrash it: measured)
 struct TraceParamsConst {
     TraceParams p;
     float4 pairs[kMaxConstSpheres];
@@ -272,6 +272,9 @@ __device__ __forceinline__ void trace_body(const TraceParams& P, const float4* _
         sweep2(pairs, gather, P.n_pad, A.path, B.path, ta, ia, tb, ib);
         if (A.alive) finish_or_continue(P, gather, s_aux, s_alb, A, ta, ia, n_seg, n_samp, n_cap, n_abs);
         if (B.alive) finish_or_continue(P, gather, s_aux, s_alb, B, tb, ib, n_seg, n_samp, n_cap, n_abs);
+        // explicit reconvergence point: with it ptxas proves the loop top converged (no BRA.DIV before
+        // the votes) and keeps the sweep's addressing / constant-bank operands on the uniform datapath
+        __syncwarp();
     }
     // warp-reduce the work counters, one atomic per warp and counter
     unsigned long long v0 = n_samp, v1 = n_seg, v2 = n_cap, v3 = n_abs;
@@ -290,14 +293,16 @@ __device__ __forceinline__ void trace_body(const TraceParams& P, const float4* _
     }
 }
 
-// K1a: geometry in the constant bank (kernel parameter).  No shared memory at all.
-template <int kBlock>
-__global__ void __launch_bounds__(kBlock) trace_kernel_const(const __grid_constant__ TraceParamsConst C) {
+// K1a: geometry in the constant bank (kernel parameter): the default for scenes of up to
+// kMaxConstSpheres spheres.  The sweep's sphere operands are uniform registers fed by LDCU; they cost
+// no register-file bandwidth, which is what bounds FFMA2 on sm_100.  No shared memory at all.
+template <int kBlock, int kMinBlocks>
+__global__ void __launch_bounds__(kBlock, kMinBlocks) trace_kernel_const(const __grid_constant__ TraceParamsConst C) {
     trace_body(C.p, C.pairs, C.p.geom);
 }
 
-// K1b: geometry staged into shared memory by one 1-D TMA bulk copy (cp.async.bulk + mbarrier);
-// the default; 32 B of shared memory per sphere (up to ~7 200 spheres in 227 KiB).
+// K1b: geometry staged into shared memory by 1-D TMA bulk copies (cp.async.bulk + mbarrier): scenes
+// too large for the parameter space; 32 B of shared memory per sphere (up to ~7 200 spheres in 227 KiB).
 template <int kBlock, int kMinBlocks>
 __global__ void __launch_bounds__(kBlock, kMinBlocks) trace_kernel_smem(const __grid_constant__ TraceParams P) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
