@@ -42,7 +42,7 @@ struct MSphere {  // the device SoA, one element
 
 struct MCamera {
     F3 p0, du, dv, c, uu, vv;
-    float tmin;
+    float tmin, tmax;
     bool defocus;
     uint32_t W, H, spp, bounce_max, k0, k1;
 };
@@ -82,17 +82,17 @@ inline F3 randomUnitVec(const Rng& g, uint32_t bounce, const uint32_t block0[4])
 
 struct Path {
     F3 o, d;
-    float tr, tg, tb, tmin_d;
+    float tr, tg, tb, len;
     int self;
     uint32_t bounce;
 };
 
-inline void setDirection(Path& p, float dx, float dy, float dz, float tmin) {
+inline void setDirection(Path& p, float dx, float dy, float dz) {
     const float len2 = std::fmaf(dz, dz, std::fmaf(dy, dy, dx * dx));
     const float len = std::sqrt(len2);
     const float inv = 1.0f / len;
     p.d = {dx * inv, dy * inv, dz * inv};
-    p.tmin_d = tmin * len;
+    p.len = len;
 }
 
 inline void cameraRay(const MCamera& c, const Rng& g, uint32_t i, uint32_t j, Path& p) {
@@ -110,14 +110,15 @@ inline void cameraRay(const MCamera& c, const Rng& g, uint32_t i, uint32_t j, Pa
         p.o = {std::fmaf(c.vv.x, b, std::fmaf(c.uu.x, a, c.c.x)), std::fmaf(c.vv.y, b, std::fmaf(c.uu.y, a, c.c.y)),
                std::fmaf(c.vv.z, b, std::fmaf(c.uu.z, a, c.c.z))};
     }
-    setDirection(p, psx - p.o.x, psy - p.o.y, psz - p.o.z, c.tmin);
+    setDirection(p, psx - p.o.x, psy - p.o.y, psz - p.o.z);
     p.tr = p.tg = p.tb = 1.0f;
     p.self = -1;
     p.bounce = 0;
 }
 
-inline void sweep(const std::vector<MSphere>& sp, const Path& p, float& t_out, int& best_out) {
-    float closest = INFINITY;
+inline void sweep(const std::vector<MSphere>& sp, const Path& p, float tmin, float tmax, float& t_out, int& best_out) {
+    const float tmin_d = tmin * p.len;  // Scene.interval in distance units
+    float closest = tmax * p.len;
     int best = -1;
     const int n = (int)sp.size();
     // per-ray constants of the expanded discriminant
@@ -140,9 +141,9 @@ inline void sweep(const std::vector<MSphere>& sp, const Path& p, float& t_out, i
         if (i == p.self) disc = h * h;
         const float sq = std::sqrt(disc);
         float t = h - sq;
-        if (!(t > p.tmin_d && t < closest)) {
+        if (!(t > tmin_d && t < closest)) {
             t = h + sq;
-            if (!(t > p.tmin_d && t < closest)) continue;
+            if (!(t > tmin_d && t < closest)) continue;
         }
         closest = t;
         best = i;
@@ -217,7 +218,7 @@ inline bool shade(const MCamera& cam, const Rng& g, const std::vector<MSphere>& 
         return true;
     }
     p.o = {px, py, pz};
-    setDirection(p, ndx, ndy, ndz, cam.tmin);
+    setDirection(p, ndx, ndy, ndz);
     p.self = best;
     return false;
 }
@@ -262,6 +263,7 @@ int orc_render_mirror(const rtz_camera* cam, const rtz_sphere* sp, uint64_t n, u
     c.p0 = f3(cam->pixel0), c.du = f3(cam->du), c.dv = f3(cam->dv), c.c = f3(cam->center);
     c.uu = f3(cam->defocus_disk_u), c.vv = f3(cam->defocus_disk_v);
     c.tmin = (float)cam->t_min;
+    c.tmax = (float)cam->t_max;
     c.defocus = cam->defocus_angle > 0;
     c.W = (uint32_t)cam->width, c.H = (uint32_t)cam->height;
     c.spp = (uint32_t)cam->samples_per_pixel, c.bounce_max = (uint32_t)cam->bounce_max;
@@ -289,13 +291,17 @@ int orc_render_mirror(const rtz_camera* cam, const rtz_sphere* sp, uint64_t n, u
             uint64_t acc[3] = {0, 0, 0};
             if (x < c.W && y < c.H && ty < tiles_y) {
                 for (uint32_t s = 0; s < c.spp; ++s) {
+                    if (c.bounce_max == 0) {  // rayColor's loop never runs: black, no hit test (camera.zig:153,181)
+                        ++k.samples;
+                        continue;
+                    }
                     Rng g{{c.k0, c.k1}, y * c.W + x, s};
                     Path p;
                     cameraRay(c, g, x, y, p);
                     for (;;) {
                         float t;
                         int best;
-                        sweep(ms, p, t, best);
+                        sweep(ms, p, c.tmin, c.tmax, t, best);
                         ++k.segments;
                         float sr, sg, sb;
                         int term;

@@ -125,6 +125,7 @@ rtz::DevCamera to_dev_camera(const rtz_camera& c, uint64_t seed) {
     d.uux = (float)c.defocus_disk_u[0], d.uuy = (float)c.defocus_disk_u[1], d.uuz = (float)c.defocus_disk_u[2];
     d.vvx = (float)c.defocus_disk_v[0], d.vvy = (float)c.defocus_disk_v[1], d.vvz = (float)c.defocus_disk_v[2];
     d.tmin = (float)c.t_min;
+    d.tmax = (float)c.t_max;
     d.defocus = c.defocus_angle > 0 ? 1 : 0;  // src/camera.zig:191
     d.width = (uint32_t)c.width, d.height = (uint32_t)c.height;
     d.spp = (uint32_t)c.samples_per_pixel, d.bounce_max = (uint32_t)c.bounce_max;
@@ -180,8 +181,11 @@ int32_t render_path(rtz_context* ctx, const rtz_camera* cam, const rtz::ShardGeo
     RTZ_CUDA(cudaMemsetAsync(ctx->accum.p, 0, 3 * n_local_pixels * sizeof(unsigned long long), ctx->stream));
     RTZ_CUDA(cudaMemsetAsync(ctx->counters.p, 0, 8 * sizeof(unsigned long long), ctx->stream));
     RTZ_CUDA(cudaEventRecord(ctx->ev[1], ctx->stream));
-    int32_t rc;
-    if (use_const) {
+    int32_t rc = RTZ_OK;
+    if (P.cam.bounce_max == 0) {
+        // `while (bounces < bounceMax)` never runs (src/camera.zig:153): every sample is black and no
+        // world.hit is made.  Nothing to trace; the zeroed sums resolve to zeros.
+    } else if (use_const) {
         static thread_local rtz::TraceParamsConst C;  // 8 KiB: keep it off the stack
         C.p = P;
         std::memcpy(C.pairs, ctx->h_pairs.data(), (size_t)ctx->n_pad * sizeof(float4));
@@ -227,9 +231,19 @@ int32_t render_path(rtz_context* ctx, const rtz_camera* cam, const rtz::ShardGeo
     if (st) {
         std::memset(st, 0, sizeof(*st));
         st->samples = ctx->h_counters[1], st->segments = ctx->h_counters[2];
+        if (P.cam.bounce_max == 0) {  // counted on the host: the kernel did not run
+            uint64_t px = 0;
+            for (uint32_t t = sg.rank; t < (uint64_t)sg.tiles_x * sg.tiles_y; t += sg.world) {
+                const uint32_t ty = t / sg.tiles_x, tx = t - ty * sg.tiles_x;
+                const uint64_t w = std::min<uint64_t>(sg.tile_w, cam->width - (uint64_t)tx * sg.tile_w);
+                const uint64_t h = std::min<uint64_t>(sg.tile_h, cam->height - (uint64_t)ty * sg.tile_h);
+                px += w * h;
+            }
+            st->samples = px * cam->samples_per_pixel;
+        }
         st->depth_capped = ctx->h_counters[3], st->absorbed = ctx->h_counters[4];
         st->sphere_tests = st->segments * (uint64_t)ctx->n_spheres;
-        st->kernel_launches = 2;
+        st->kernel_launches = P.cam.bounce_max == 0 ? 1 : 2;
         float ms = 0;
         cudaEventElapsedTime(&ms, ctx->ev[1], ctx->ev[2]), st->trace_ms = ms;
         cudaEventElapsedTime(&ms, ctx->ev[2], ctx->ev[3]), st->resolve_ms = ms;
@@ -545,7 +559,7 @@ int32_t rtz_probe_scatter(const rtz_sphere* sp, uint64_t n, int32_t index, const
     if (rc != RTZ_OK) return rc;
     rtz_camera cam;
     std::memset(&cam, 0, sizeof(cam));
-    cam.t_min = 1e-3, cam.bounce_max = 0xFFFFFFFFull, cam.samples_per_pixel = 1, cam.width = cam.height = 1;
+    cam.t_min = 1e-3, cam.t_max = INFINITY, cam.bounce_max = 0xFFFFFFFFull, cam.samples_per_pixel = 1, cam.width = cam.height = 1;
     const rtz::DevCamera dc = to_dev_camera(cam, seed);
     rtz::ProbeScatterOut* dout;
     RTZ_CUDA(cudaMalloc(&dout, sizeof(*dout)));

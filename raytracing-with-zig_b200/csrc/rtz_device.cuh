@@ -44,7 +44,7 @@ struct DevCamera {
     float cx, cy, cz;        // center
     float uux, uuy, uuz;     // defocusDiskU
     float vvx, vvy, vvz;     // defocusDiskV
-    float tmin;              // Scene.interval.min
+    float tmin, tmax;        // Scene.interval (src/Scene.zig:21): (1e-3, +inf) by default
     int defocus;             // defocusAngle > 0
     uint32_t width, height, spp, bounce_max;
     uint32_t key0, key1;     // Philox key = seed
@@ -112,18 +112,18 @@ struct Path {
     float ox, oy, oz;   // ray origin
     float dx, dy, dz;   // ray direction, UNIT length
     float tr, tg, tb;   // throughput (returnColor of rayColor)
-    float tmin_d;       // t_min * |d_unnormalised|
+    float len;          // |d| before normalisation: the hit interval in distance units is (t_min*len, t_max*len)
     int self;           // sphere the origin lies on, -1 for camera rays
     uint32_t bounce;    // scatters so far
 };
 
-// Store an un-normalised direction: normalise, rescale t_min (Q7/Q8).
-__device__ __forceinline__ void set_direction(Path& p, float dx, float dy, float dz, float tmin) {
+// Store an un-normalised direction: normalise and keep its length, which rescales Scene.interval (Q7/Q8).
+__device__ __forceinline__ void set_direction(Path& p, float dx, float dy, float dz) {
     const float len2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
     const float len = sqrtf(len2);
     const float inv = 1.0f / len;
     p.dx = dx * inv, p.dy = dy * inv, p.dz = dz * inv;
-    p.tmin_d = tmin * len;
+    p.len = len;
 }
 
 // Camera.getRay (src/camera.zig:187-200) for pixel (i,j), sample k.sample.
@@ -142,7 +142,7 @@ __device__ __forceinline__ void camera_ray(const DevCamera& c, const RngKey& k, 
         p.oy = fmaf(c.vvy, b, fmaf(c.uuy, a, c.cy));
         p.oz = fmaf(c.vvz, b, fmaf(c.uuz, a, c.cz));
     }
-    set_direction(p, psx - p.ox, psy - p.oy, psz - p.oz, c.tmin);
+    set_direction(p, psx - p.ox, psy - p.oy, psz - p.oz);
     p.tr = p.tg = p.tb = 1.0f;
     p.self = -1;
     p.bounce = 0;
@@ -187,13 +187,13 @@ __device__ __forceinline__ float expanded_disc(float cx, float cy, float cz, flo
     return fmaf(h, h, w);
 }
 // root of a candidate from the direct form (src/sphere.zig:27-42); g = {cx, cy, cz, -r^2}
-__device__ __forceinline__ void candidate_root(const float4 g, float nr2, int i, const Path& p, float& closest,
-                                               int& best) {
+__device__ __forceinline__ void candidate_root(const float4 g, float nr2, int i, const Path& p, float tmin_d,
+                                               float& closest, int& best) {
     const float ocx = g.x - p.ox, ocy = g.y - p.oy, ocz = g.z - p.oz;
     const float h = fmaf(p.dz, ocz, fmaf(p.dy, ocy, p.dx * ocx));
     const float c = fmaf(ocz, ocz, fmaf(ocy, ocy, fmaf(ocx, ocx, nr2)));
     const float disc = fmaf(h, h, -c);
-    if (disc >= 0.0f) slow_path(h, disc, i, p.self, p.tmin_d, closest, best);
+    if (disc >= 0.0f) slow_path(h, disc, i, p.self, tmin_d, closest, best);
 }
 
 // scalar sweep over plain rows {cx, cy, cz, -r^2} + the pair layout's w: serves the one-ray probes;
@@ -203,14 +203,15 @@ __device__ __forceinline__ float pair_w(const float4* __restrict__ pairs, int i)
     return (i & 1) ? p1.w : p1.z;
 }
 __device__ __forceinline__ void sweep_rows(const float4* __restrict__ geo, const float4* __restrict__ pairs, int first,
-                                           int n, const Path& p, float& t_out, int& best_out) {
-    float closest = __int_as_float(0x7f800000);  // +inf
+                                           int n, const Path& p, float tmin, float tmax, float& t_out, int& best_out) {
+    const float tmin_d = tmin * p.len;
+    float closest = tmax * p.len;  // Interval(t_min, t_max) in distance units; +inf stays +inf
     int best = -1;
     const RayK k = ray_constants(p);
     for (int i = first; i < first + n; ++i) {
         const float4 g = geo[i];
         const float d = expanded_disc(g.x, g.y, g.z, pair_w(pairs, i), p, k);
-        if (!(__float_as_uint(d) >> 31)) candidate_root(g, g.w, i, p, closest, best);
+        if (!(__float_as_uint(d) >> 31)) candidate_root(g, g.w, i, p, tmin_d, closest, best);
     }
     t_out = closest;
     best_out = best;
@@ -297,7 +298,7 @@ __device__ __forceinline__ bool shade(const DevCamera& cam, const RngKey& k, con
         return true;
     }
     p.ox = px, p.oy = py, p.oz = pz;
-    set_direction(p, ndx, ndy, ndz, cam.tmin);
+    set_direction(p, ndx, ndy, ndz);
     p.self = best;
     return false;
 }

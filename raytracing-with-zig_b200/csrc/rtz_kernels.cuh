@@ -115,13 +115,13 @@ struct Slot {
 // (src/sphere.zig:35-42) with the shrinking t_max of HittableList.hit (src/hittable.zig:66-73).
 // `gather[i]` = {cx, cy, cz, -r^2} serves the per-lane (divergent) lookups.
 __device__ __forceinline__ void resolve_candidates(const float4* __restrict__ gather, unsigned cand, int base, int cnt,
-                                                   const Path& p, float& closest, int& best) {
+                                                   const Path& p, float tmin_d, float& closest, int& best) {
     while (cand) {
         const int bit = 31 - __clz(cand);  // highest bit = lowest sphere index: ascending order
         cand &= ~(1u << bit);
         const int i = base + (cnt - 1 - bit);
         const float4 g = gather[i];
-        candidate_root(g, g.w, i, p, closest, best);
+        candidate_root(g, g.w, i, p, tmin_d, closest, best);
     }
 }
 
@@ -150,9 +150,12 @@ __device__ __forceinline__ void test_pair(const float4 p0, const float4 p1, cons
 // or the constant bank): per sphere pair 2 LDS.128 + 2 x (7 FFMA2 + 1 FADD2 + 2 SHF) for FOUR tests.
 // n_pad is a multiple of 8; padding spheres have w = -inf -> disc = -inf -> never a candidate.
 __device__ __forceinline__ void sweep2(const float4* __restrict__ pairs, const float4* __restrict__ gather, int n_pad,
-                                       const Path& a, const Path& b, float& ta, int& ia, float& tb, int& ib) {
+                                       float tmin, float tmax, const Path& a, const Path& b, float& ta, int& ia,
+                                       float& tb, int& ib) {
     const RayK ka = ray_constants(a), kb = ray_constants(b);
-    float ca = __int_as_float(0x7f800000), cb = ca;
+    // Interval(t_min, t_max) of Scene.interval in distance units (directions are unit length)
+    const float tmin_a = tmin * a.len, tmin_b = tmin * b.len;
+    float ca = tmax * a.len, cb = tmax * b.len;
     int ba = -1, bb = -1;
     for (int base = 0; base < n_pad; base += 32) {
         const int cnt = min(32, n_pad - base);
@@ -169,8 +172,8 @@ __device__ __forceinline__ void sweep2(const float4* __restrict__ pairs, const f
         }
         const unsigned canda = ~ma, candb = ~mb;
         if (canda | candb) {
-            resolve_candidates(gather, canda, base, cnt, a, ca, ba);
-            resolve_candidates(gather, candb, base, cnt, b, cb, bb);
+            resolve_candidates(gather, canda, base, cnt, a, tmin_a, ca, ba);
+            resolve_candidates(gather, candb, base, cnt, b, tmin_b, cb, bb);
         }
     }
     ta = ca, ia = ba, tb = cb, ib = bb;
@@ -211,7 +214,7 @@ __device__ __forceinline__ void trace_body(const TraceParams& P, const float4* _
     A.lp = B.lp = 0;
     A.key = B.key = RngKey{cam.key0, cam.key1, 0u, 0u};
     A.path.ox = A.path.oy = A.path.oz = 0.f, A.path.dx = A.path.dy = 0.f, A.path.dz = 1.f;
-    A.path.tr = A.path.tg = A.path.tb = 0.f, A.path.tmin_d = 0.f, A.path.self = -1, A.path.bounce = 0;
+    A.path.tr = A.path.tg = A.path.tb = 0.f, A.path.len = 1.f, A.path.self = -1, A.path.bounce = 0;
     B.path = A.path;
 
     // warp-uniform chunk state
@@ -269,7 +272,7 @@ __device__ __forceinline__ void trace_body(const TraceParams& P, const float4* _
         if (__ballot_sync(0xFFFFFFFFu, A.alive || B.alive) == 0u) break;  // queue drained, every path finished
         float ta, tb;
         int ia, ib;
-        sweep2(pairs, gather, P.n_pad, A.path, B.path, ta, ia, tb, ib);
+        sweep2(pairs, gather, P.n_pad, cam.tmin, cam.tmax, A.path, B.path, ta, ia, tb, ib);
         if (A.alive) finish_or_continue(P, gather, s_aux, s_alb, A, ta, ia, n_seg, n_samp, n_cap, n_abs);
         if (B.alive) finish_or_continue(P, gather, s_aux, s_alb, B, tb, ib, n_seg, n_samp, n_cap, n_abs);
         // explicit reconvergence point: with it ptxas proves the loop top converged (no BRA.DIV before
@@ -446,14 +449,11 @@ __global__ void probe_hit_kernel(const float4* geom, const float4* pairs, const 
                                  float dx, float dy, float dz, float tmin, float tmax, ProbeHitOut* out) {
     Path p;
     p.ox = ox, p.oy = oy, p.oz = oz, p.self = -1, p.bounce = 0, p.tr = p.tg = p.tb = 1.f;
-    set_direction(p, dx, dy, dz, tmin);
-    const float len = sqrtf(fmaf(dz, dz, fmaf(dy, dy, dx * dx)));
+    set_direction(p, dx, dy, dz);
     float t;
     int best;
-    sweep_rows(geom, pairs, 0, n_pad, p, t, best);
-    // the render kernel's t_max is +inf; a finite t_max (unit tests) is applied here
-    if (best >= 0 && !(t < tmax * len)) best = -1;
-    out->hit = best >= 0, out->index = best, out->len = len, out->t = t;
+    sweep_rows(geom, pairs, 0, n_pad, p, tmin, tmax, t, best);
+    out->hit = best >= 0, out->index = best, out->len = p.len, out->t = t;
     if (best >= 0) {
         const float gx = geom[best].x, gy = geom[best].y, gz = geom[best].z;
         const float px = fmaf(t, p.dx, p.ox), py = fmaf(t, p.dy, p.oy), pz = fmaf(t, p.dz, p.oz);
@@ -474,10 +474,10 @@ __global__ void probe_scatter_kernel(DevCamera cam, const float4* geom, const fl
                                      uint32_t pixel, uint32_t sample, uint32_t bounce, ProbeScatterOut* out) {
     Path p;
     p.ox = ox, p.oy = oy, p.oz = oz, p.self = -1, p.bounce = bounce, p.tr = p.tg = p.tb = 1.f;
-    set_direction(p, dx, dy, dz, cam.tmin);
+    set_direction(p, dx, dy, dz);
     float t;
     int best;
-    sweep_rows(geom, pairs, index, 1, p, t, best);  // Sphere.hit on that one sphere
+    sweep_rows(geom, pairs, index, 1, p, cam.tmin, cam.tmax, t, best);  // Sphere.hit on that one sphere
     out->scattered = 0, out->term = -1;
     if (best < 0) return;
     RngKey k{cam.key0, cam.key1, pixel, sample};
@@ -488,7 +488,7 @@ __global__ void probe_scatter_kernel(DevCamera cam, const float4* geom, const fl
     if (done) return;
     out->scattered = 1;
     out->o[0] = p.ox, out->o[1] = p.oy, out->o[2] = p.oz;
-    out->len = p.tmin_d / cam.tmin;  // |direction| before normalisation
+    out->len = p.len;  // |direction| before normalisation
     out->d[0] = p.dx, out->d[1] = p.dy, out->d[2] = p.dz;
     out->att[0] = p.tr, out->att[1] = p.tg, out->att[2] = p.tb;
 }

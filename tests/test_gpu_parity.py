@@ -201,6 +201,20 @@ def test_edge_cases(pkg, gpu, orc):
     mrgb, _, mst = _mirror(orc, cam, sp, n, 3)
     assert st.segments == st.samples and np.array_equal(rgb.reshape(-1, 3), mrgb)
     assert st.depth_capped == mst.depth_capped > 0
+    # bounce_max = 0: rayColor's loop never runs -> black image, no hit test at all
+    cam = R.build_camera(40, 16.0 / 9.0, (0, 0, 0), (0, 0, -1), 90, spp=3, bounce_max=0, seed=3)
+    rgb, st = pkg.render_host(cam, sp, n)
+    mrgb, _, mst = _mirror(orc, cam, sp, n, 3)
+    assert st.segments == 0 == mst.segments and st.samples == mst.samples == 40 * 22 * 3 and not rgb.any() and not mrgb.any()
+    # finite Scene.interval.max: hits beyond t_max (in units of |dir|) are ignored
+    cam = R.build_camera(96, 16.0 / 9.0, (-2, 2, 1), (0, 0, -1), 20, spp=4, seed=3)
+    cam.t_max = 0.9
+    rgb, st = pkg.render_host(cam, sp, n)
+    mrgb, _, mst = _mirror(orc, cam, sp, n, 3)
+    cam.t_max = float("inf")
+    rgb_inf, st_inf = pkg.render_host(cam, sp, n)
+    assert np.array_equal(rgb.reshape(-1, 3), mrgb) and st.segments == mst.segments
+    assert st.segments < st_inf.segments and not np.array_equal(rgb, rgb_inf)
     # odd sphere count (SoA padding), ragged width
     cam = R.build_camera(37, 1.3, (-2, 2, 1), (0, 0, -1), 40, spp=5, seed=11)
     rgb, st = pkg.render_host(cam, sp, 3)

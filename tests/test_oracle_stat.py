@@ -75,3 +75,22 @@ def test_chapter13_scene_mirror_vs_f64_reference(orc, preset):
     b, _ = _ref(orc, cam, sp, n, 2)
     _gates(m, mst, a, ast, b)
     assert abs(ast.segments / ast.samples - 3.584) / 3.584 < 0.03
+
+
+def test_finite_t_max_and_zero_bounces_mirror_vs_reference(orc):
+    """Scene.interval is editable in the reference (src/Scene.zig:21): a finite max and bounceMax = 0
+    behave the same in the device mirror and in the f64 restatement."""
+    sp, n = R.chapter13_scene()
+    cam = R.build_camera(160, 16.0 / 9.0, (-2, 2, 1), (0, 0, -1), 20, spp=64)
+    cam.t_max = 0.9
+    m, mst = _mirror(orc, cam, sp, n, 5)
+    a, ast = _ref(orc, cam, sp, n, 1)
+    b, _ = _ref(orc, cam, sp, n, 2)
+    _gates(m, mst, a, ast, b)
+    cam.t_max = float("inf")
+    full, fst = _mirror(orc, cam, sp, n, 5)
+    assert mst.segments < fst.segments
+    cam.bounce_max = 0
+    z, zst = _mirror(orc, cam, sp, n, 5)
+    za, zast = _ref(orc, cam, sp, n, 1)
+    assert not z.any() and not za.any() and zst.segments == 0 == zast.segments and zst.samples == zast.samples
