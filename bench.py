@@ -45,7 +45,7 @@ WORKLOADS = {
     "smoke": (400, 10, "reference test render: final scene 400x225, 10 spp (dev only)"),
 }
 FLOP_PER_TEST = 17.0  # SURVEY.md §8d / BASELINE.md §3
-TILE = (16, 16)
+TILE = (32, 8)
 
 
 def measured_peaks():
@@ -332,7 +332,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
     ap.add_argument("--spp", type=int, default=0, help="override samples per pixel (dev only; invalidates the headline)")
-    ap.add_argument("--ref-spp", type=int, default=8, help="spp of the bounded CPU sample (cost per sample does not depend on spp)")
+    ap.add_argument("--ref-spp", type=int, default=48, help="spp of the bounded CPU sample (cost per sample does not depend on spp)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
