@@ -9,7 +9,10 @@ import ctypes as C
 from pathlib import Path
 
 PKG = Path(__file__).resolve().parent
-LIB_PATH = PKG / "csrc" / "librtz.so"
+import os
+
+# RTZ_LIB=<path> loads another build of the same ABI (A/B timing of kernel changes inside one GPU call)
+LIB_PATH = Path(os.environ["RTZ_LIB"]) if os.environ.get("RTZ_LIB") else PKG / "csrc" / "librtz.so"
 
 D3 = C.c_double * 3
 
