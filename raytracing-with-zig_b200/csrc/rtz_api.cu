@@ -190,7 +190,9 @@ int32_t render_path(rtz_context* ctx, const rtz_camera* cam, const rtz::ShardGeo
         C.p = P;
         std::memcpy(C.pairs, ctx->h_pairs.data(), (size_t)ctx->n_pad * sizeof(float4));
         // <128,6> (80 registers, 24 warps/SM) is the measured best; the uniform loads want occupancy
-        if (ctx->variant == 1)
+        if (ctx->variant == 4)  // experimental: 4 paths per thread, path state parked in shared memory
+            rc = launch_trace(ctx, rtz::trace_kernel_const_parked<4, 128, 6>, C, P.n_chunks, 128, 0);
+        else if (ctx->variant == 1)
             rc = launch_trace(ctx, rtz::trace_kernel_const<256, 3>, C, P.n_chunks, 256, 0);
         else if (ctx->variant == 2)
             rc = launch_trace(ctx, rtz::trace_kernel_const<128, 5>, C, P.n_chunks, 128, 0);

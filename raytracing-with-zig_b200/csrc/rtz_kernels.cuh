@@ -92,12 +92,14 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t phase) {
 // chunk at once (path regeneration), so the sphere sweep — 99 % of the work — always runs with
 // full warps except while the queue drains.
 //
-// The sweep evaluates both paths of a thread with packed FP32x2 instructions (FADD2 / FMUL2 /
-// FFMA2, new on sm_100): per sphere 2 broadcast LDS.128 + 10 packed FP ops + 2 funnel shifts that
-// append the discriminants' sign bits to per-path candidate masks.  The FP32 pipe executes a
-// packed op in two passes, so the 10 packed ops (17 FLOP x 2 tests) are the floor and the other
-// 4 instructions issue in their shadow.  Roots are only evaluated for the mask's candidates, in
-// ascending sphere order, after each block of 32 spheres.
+// The sweep tests ONE path against a PAIR of spheres per packed FP32x2 instruction (FFMA2 / FADD2, new on
+// sm_100): per sphere pair and path 7 FFMA2 + 1 FADD2 + 2 funnel shifts that append the discriminants'
+// sign bits to the path's candidate mask, plus 4 uniform loads (LDCU.64) shared by the paths of the
+// thread.  Measured on B200 (tools/ubench/sweep_ops.cu, shadow.cu, ldcu_cost.cu): a packed op holds the
+// FMA pipe for 2.06 cycles and every other instruction of the loop still costs 0.3-0.75 issue cycles in
+// its shadow, so the loop runs at 10.4 cycles per ray-sphere test against 8 for the packed ops alone.
+// Roots are only evaluated for the mask's candidates, in ascending sphere order, after each block of
+// 32 spheres.
 //
 // Finished samples are converted to 32.32 fixed point and added to the pixel with 64-bit integer
 // REDs; integer addition commutes, so the image is bit-identical for any schedule, tile size or
@@ -149,12 +151,16 @@ __device__ __forceinline__ void test_pair(const float4 p0, const float4 p1, cons
 // HittableList.hit for the two paths of a thread.  `pairs` is warp-uniform storage (shared memory
 // or the constant bank): per sphere pair 2 LDS.128 + 2 x (7 FFMA2 + 1 FADD2 + 2 SHF) for FOUR tests.
 // n_pad is a multiple of 8; padding spheres have w = -inf -> disc = -inf -> never a candidate.
+// kConstBank selects two register-allocation nudges that were measured per kernel (same arithmetic):
+// the constant-bank kernel pins 2*o (+0.8 %), the shared-memory kernel forms t_min*len late (+4 % at N = 1024).
+template <bool kConstBank>
 __device__ __forceinline__ void sweep2(const float4* __restrict__ pairs, const float4* __restrict__ gather, int n_pad,
                                        float tmin, float tmax, const Path& a, const Path& b, float& ta, int& ia,
                                        float& tb, int& ib) {
-    const RayK ka = ray_constants(a), kb = ray_constants(b);
+    RayK ka = ray_constants(a), kb = ray_constants(b);
+    // pin 2*o in registers: left alone, ptxas keeps o and re-adds it for every block of 32 spheres
+    if (kConstBank) asm volatile("" : "+f"(ka.tx), "+f"(ka.ty), "+f"(ka.tz), "+f"(kb.tx), "+f"(kb.ty), "+f"(kb.tz));
     // Interval(t_min, t_max) of Scene.interval in distance units (directions are unit length)
-    const float tmin_a = tmin * a.len, tmin_b = tmin * b.len;
     float ca = tmax * a.len, cb = tmax * b.len;
     int ba = -1, bb = -1;
     for (int base = 0; base < n_pad; base += 32) {
@@ -172,8 +178,12 @@ __device__ __forceinline__ void sweep2(const float4* __restrict__ pairs, const f
         }
         const unsigned canda = ~ma, candb = ~mb;
         if (canda | candb) {
-            resolve_candidates(gather, canda, base, cnt, a, tmin_a, ca, ba);
-            resolve_candidates(gather, candb, base, cnt, b, tmin_b, cb, bb);
+            // t_min * len is formed HERE, behind an opaque copy, so that it does not occupy two more
+            // registers across the whole sweep of the shared-memory kernel (96 registers at 5 CTAs per SM)
+            float la = a.len, lb = b.len;
+            if (!kConstBank) asm volatile("" : "+f"(la), "+f"(lb));
+            resolve_candidates(gather, canda, base, cnt, a, tmin * la, ca, ba);
+            resolve_candidates(gather, candb, base, cnt, b, tmin * lb, cb, bb);
         }
     }
     ta = ca, ia = ba, tb = cb, ib = bb;
@@ -200,6 +210,7 @@ __device__ __forceinline__ void finish_or_continue(const TraceParams& P, const f
 
 // The body shared by the two kernels below.  `geo` is the warp-uniform geometry the sweep reads,
 // `gather` the copy for per-lane lookups (candidate roots, hit records).
+template <bool kConstBank>
 __device__ __forceinline__ void trace_body(const TraceParams& P, const float4* __restrict__ pairs,
                                            const float4* __restrict__ gather) {
     // material rows are touched once per HIT (not per test): they stay in global memory / L1
@@ -272,7 +283,7 @@ __device__ __forceinline__ void trace_body(const TraceParams& P, const float4* _
         if (__ballot_sync(0xFFFFFFFFu, A.alive || B.alive) == 0u) break;  // queue drained, every path finished
         float ta, tb;
         int ia, ib;
-        sweep2(pairs, gather, P.n_pad, cam.tmin, cam.tmax, A.path, B.path, ta, ia, tb, ib);
+        sweep2<kConstBank>(pairs, gather, P.n_pad, cam.tmin, cam.tmax, A.path, B.path, ta, ia, tb, ib);
         if (A.alive) finish_or_continue(P, gather, s_aux, s_alb, A, ta, ia, n_seg, n_samp, n_cap, n_abs);
         if (B.alive) finish_or_continue(P, gather, s_aux, s_alb, B, tb, ib, n_seg, n_samp, n_cap, n_abs);
         // explicit reconvergence point: with it ptxas proves the loop top converged (no BRA.DIV before
@@ -296,12 +307,262 @@ __device__ __forceinline__ void trace_body(const TraceParams& P, const float4* _
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// K1 with R paths per thread and the path state PARKED in shared memory.
+//
+// EXPERIMENTAL (RTZ_VARIANT=4; the two-path register kernel below stays the default).  The four LDCU.64
+// of a sphere pair are shared by the R paths of a thread, so R = 4 brings the sweep loop from 10.4 to 9.7
+// cycles per test in isolation.  Four paths need 4 x 8 sweep constants in registers, so everything the
+// sweep does not read (origin, throughput, RNG counter, pixel, bounce) lives in shared memory, one word
+// per (field, slot, thread): bank = thread, never a conflict, and the slot index may be a per-lane
+// variable.  Shading runs ONE slot at a time through a single copy of its code; camera rays are
+// generated by all lanes of the warp for whichever lane owns the free slot.  Measured on C3: the same
+// 159 ms as the register kernel (the extra shared-memory traffic eats the saving of the loop), and the
+// same bytes: tests/test_gpu_parity.py::test_image_is_independent_of_the_schedule.
+// ---------------------------------------------------------------------------------------------
+enum ParkField { kOx, kOy, kOz, kDx, kDy, kDz, kTr, kTg, kTb, kLen, kSelf, kBounce, kPixel, kSample, kLp, kParkFields };
+
+template <int R, int kBlock>
+struct Park {
+    float* base;  // [kParkFields][R][kBlock]
+    __device__ __forceinline__ float& f(int field, int slot) const {
+        return base[(field * R + slot) * kBlock + threadIdx.x];
+    }
+    __device__ __forceinline__ uint32_t& u(int field, int slot) const {
+        return reinterpret_cast<uint32_t*>(base)[(field * R + slot) * kBlock + threadIdx.x];
+    }
+    // re-read a parked word inside a rarely executed branch: `volatile` keeps the compiler from
+    // holding the value in a register across the sweep instead
+    __device__ __forceinline__ float fv(int field, int slot) const {
+        return *reinterpret_cast<volatile float*>(&base[(field * R + slot) * kBlock + threadIdx.x]);
+    }
+    __device__ __forceinline__ void store_ray(int s, const Path& p) const {
+        f(kOx, s) = p.ox, f(kOy, s) = p.oy, f(kOz, s) = p.oz;
+        f(kDx, s) = p.dx, f(kDy, s) = p.dy, f(kDz, s) = p.dz;
+        f(kTr, s) = p.tr, f(kTg, s) = p.tg, f(kTb, s) = p.tb;
+        f(kLen, s) = p.len, u(kSelf, s) = (uint32_t)p.self, u(kBounce, s) = p.bounce;
+    }
+    __device__ __forceinline__ void load_ray(int s, Path& p) const {
+        p.ox = f(kOx, s), p.oy = f(kOy, s), p.oz = f(kOz, s);
+        p.dx = f(kDx, s), p.dy = f(kDy, s), p.dz = f(kDz, s);
+        p.tr = f(kTr, s), p.tg = f(kTg, s), p.tb = f(kTb, s);
+        p.len = f(kLen, s), p.self = (int)u(kSelf, s), p.bounce = u(kBounce, s);
+    }
+};
+
+// what the sweep keeps in registers per path
+struct Hot {
+    float dx, dy, dz, k1, tx, ty, tz, nk2;
+};
+
+__device__ __forceinline__ void test_pair_hot(const float4 p0, const float4 p1, const Hot& q, unsigned& mask) {
+    const float2 cx = make_float2(p0.x, p0.y), cy = make_float2(p0.z, p0.w);
+    const float2 cz = make_float2(p1.x, p1.y), cw = make_float2(p1.z, p1.w);
+    float2 h = __ffma2_rn(make_float2(q.dx, q.dx), cx, make_float2(q.k1, q.k1));
+    h = __ffma2_rn(make_float2(q.dy, q.dy), cy, h);
+    h = __ffma2_rn(make_float2(q.dz, q.dz), cz, h);
+    float2 w = __ffma2_rn(make_float2(q.tx, q.tx), cx, make_float2(q.nk2, q.nk2));
+    w = __ffma2_rn(make_float2(q.ty, q.ty), cy, w);
+    w = __ffma2_rn(make_float2(q.tz, q.tz), cz, w);
+    w = __fadd2_rn(w, cw);
+    const float2 disc = __ffma2_rn(h, h, w);
+    mask = __funnelshift_l(__float_as_uint(disc.x), mask, 1);
+    mask = __funnelshift_l(__float_as_uint(disc.y), mask, 1);
+}
+
+template <int R, int kBlock>
+__device__ __forceinline__ void trace_body_parked(const TraceParams& P, const float4* __restrict__ pairs,
+                                                  const float4* __restrict__ gather, float* park_mem,
+                                                  uint8_t* todo_mem) {
+    const Park<R, kBlock> park{park_mem};
+    uint8_t* todo = todo_mem + (threadIdx.x >> 5) * (32 * R);  // this warp's list of free slots
+    const float4* s_aux = P.aux;
+    const float4* s_alb = P.albedo;
+    const unsigned lane = threadIdx.x & 31u;
+    const unsigned lt_mask = (1u << lane) - 1u;
+    const DevCamera& cam = P.cam;
+    constexpr unsigned kFull = (1u << R) - 1u;
+
+    unsigned alive = 0;  // bit s = slot s carries a live path
+    {
+        Path idle;  // what a slot without a path sweeps (its result is ignored)
+        idle.ox = idle.oy = idle.oz = 0.f, idle.dx = idle.dy = 0.f, idle.dz = 1.f;
+        idle.tr = idle.tg = idle.tb = 0.f, idle.len = 1.f, idle.self = -1, idle.bounce = 0;
+#pragma unroll
+        for (int s = 0; s < R; ++s) park.store_ray(s, idle);
+    }
+
+    uint32_t ch_lp = 0, ch_x = 0, ch_y = 0, ch_next = 0, ch_end = 0;  // warp-uniform chunk state
+    bool exhausted = false;
+    unsigned long long n_seg = 0;
+    uint32_t n_samp = 0, n_cap = 0, n_abs = 0;
+
+    for (;;) {
+        // ---- path regeneration, warp-cooperative: the free slots of the whole warp are ranked (slot-
+        // major), published in `todo`, and the camera rays of the chunk's next samples are generated
+        // 32 at a time by ALL lanes, each writing into the owner's parked slot.  Which lane computes a
+        // ray does not matter: its random numbers depend on (pixel, sample) only.
+        for (;;) {
+            const unsigned dead = ~alive & kFull;
+            unsigned bal[R];
+            uint32_t total = 0;
+#pragma unroll
+            for (int s = 0; s < R; ++s) {
+                bal[s] = __ballot_sync(0xFFFFFFFFu, (dead >> s) & 1u);
+                total += __popc(bal[s]);
+            }
+            if (total == 0u || exhausted) break;
+            if (ch_next >= ch_end) {
+                unsigned long long cid = 0;
+                if (lane == 0) cid = atomicAdd(P.counter, 1ULL);
+                cid = __shfl_sync(0xFFFFFFFFu, cid, 0);
+                if (__any_sync(0xFFFFFFFFu, cid >= P.n_chunks)) {
+                    exhausted = true;
+                    break;
+                }
+                ch_lp = (uint32_t)(cid / P.chunks_per_pixel);
+                const uint32_t part = (uint32_t)(cid - (unsigned long long)ch_lp * P.chunks_per_pixel);
+                const bool inside = local_to_global(P.sh, cam.width, cam.height, ch_lp, ch_x, ch_y);
+                if (__any_sync(0xFFFFFFFFu, !inside)) continue;  // tile padding
+                ch_next = part * P.chunk;
+                ch_end = min(ch_next + P.chunk, cam.spp);
+            }
+            const uint32_t n = min(total, ch_end - ch_next);
+            uint32_t before = 0;
+#pragma unroll
+            for (int s = 0; s < R; ++s) {
+                const uint32_t r = before + __popc(bal[s] & lt_mask);
+                if (((dead >> s) & 1u) && r < n) {
+                    todo[r] = (uint8_t)(lane | (s << 5));
+                    alive |= 1u << s;
+                }
+                before += __popc(bal[s]);
+            }
+            __syncwarp();
+            for (uint32_t j = lane; j < n; j += 32u) {
+                const unsigned id = todo[j];
+                const int owner = (int)(id & 31u) - (int)lane, s = (int)(id >> 5);  // owner as an offset from this thread
+                const RngKey key{cam.key0, cam.key1, ch_y * cam.width + ch_x, ch_next + j};
+                Path p;
+                camera_ray(cam, key, ch_x, ch_y, p);
+                const Park<R, kBlock> dst{park_mem + owner};
+                dst.store_ray(s, p);
+                dst.u(kPixel, s) = key.pixel, dst.u(kSample, s) = key.sample, dst.u(kLp, s) = ch_lp;
+            }
+            ch_next += n;
+            __syncwarp();
+        }
+        if (__ballot_sync(0xFFFFFFFFu, alive != 0u) == 0u) break;  // queue drained, every path finished
+
+        // ---- HittableList.hit for the R paths of the thread ----
+        Hot hot[R];
+        float closest[R];
+        int best[R];
+#pragma unroll
+        for (int s = 0; s < R; ++s) {
+            Path p;
+            p.ox = park.f(kOx, s), p.oy = park.f(kOy, s), p.oz = park.f(kOz, s);
+            p.dx = park.f(kDx, s), p.dy = park.f(kDy, s), p.dz = park.f(kDz, s);
+            RayK k = ray_constants(p);
+            // pin 2*o in registers: left alone, ptxas keeps o and re-adds it inside the sweep loop
+            asm volatile("" : "+f"(k.tx), "+f"(k.ty), "+f"(k.tz));
+            hot[s] = Hot{p.dx, p.dy, p.dz, k.k1, k.tx, k.ty, k.tz, k.nk2};
+            closest[s] = cam.tmax * park.f(kLen, s);
+            best[s] = -1;
+        }
+        for (int base = 0; base < P.n_pad; base += 32) {
+            const int cnt = min(32, P.n_pad - base);
+            unsigned m[R];
+#pragma unroll
+            for (int s = 0; s < R; ++s) m[s] = 0xFFFFFFFFu;  // 1 = miss
+            const float4* g = pairs + base;
+#pragma unroll 1
+            for (int k = 0; k < cnt; k += 8) {
+#pragma unroll
+                for (int u = 0; u < 8; u += 2) {
+                    const float4 p0 = g[k + u], p1 = g[k + u + 1];
+#pragma unroll
+                    for (int s = 0; s < R; ++s) test_pair_hot(p0, p1, hot[s], m[s]);
+                }
+            }
+            unsigned any = 0;
+#pragma unroll
+            for (int s = 0; s < R; ++s) any |= ~m[s];
+            if (any) {
+#pragma unroll
+                for (int s = 0; s < R; ++s) {
+                    if (~m[s]) {
+                        Path p;
+                        p.ox = park.fv(kOx, s), p.oy = park.fv(kOy, s), p.oz = park.fv(kOz, s);
+                        p.dx = hot[s].dx, p.dy = hot[s].dy, p.dz = hot[s].dz;
+                        p.self = __float_as_int(park.fv(kSelf, s));
+                        const float tmin_d = cam.tmin * park.fv(kLen, s);
+                        resolve_candidates(gather, ~m[s], base, cnt, p, tmin_d, closest[s], best[s]);
+                    }
+                }
+            }
+        }
+
+        // ---- shading, one slot at a time through one copy of the code ----
+#pragma unroll 1
+        for (int s = 0; s < R; ++s) {
+            float t = closest[0];
+            int b = best[0];
+#pragma unroll
+            for (int q = 1; q < R; ++q)
+                if (s == q) t = closest[q], b = best[q];
+            if ((alive >> s) & 1u) {
+                ++n_seg;
+                Path p;
+                park.load_ray(s, p);
+                const RngKey key{cam.key0, cam.key1, park.u(kPixel, s), park.u(kSample, s)};
+                float sr, sg, sb;
+                int term;
+                if (shade(cam, key, gather, s_aux, s_alb, p, t, b, sr, sg, sb, term)) {
+                    const unsigned long long fr = to_fixed(sr), fg = to_fixed(sg), fb = to_fixed(sb);
+                    unsigned long long* px = P.accum + 3ull * park.u(kLp, s);
+                    if (fr) atomicAdd(px + 0, fr);
+                    if (fg) atomicAdd(px + 1, fg);
+                    if (fb) atomicAdd(px + 2, fb);
+                    ++n_samp;
+                    n_cap += (term == 2), n_abs += (term == 1);
+                    alive &= ~(1u << s);
+                } else {
+                    park.store_ray(s, p);
+                }
+            }
+            __syncwarp();
+        }
+    }
+    unsigned long long v0 = n_samp, v1 = n_seg, v2 = n_cap, v3 = n_abs;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        v0 += __shfl_xor_sync(0xFFFFFFFFu, v0, o);
+        v1 += __shfl_xor_sync(0xFFFFFFFFu, v1, o);
+        v2 += __shfl_xor_sync(0xFFFFFFFFu, v2, o);
+        v3 += __shfl_xor_sync(0xFFFFFFFFu, v3, o);
+    }
+    if (lane == 0) {
+        atomicAdd(P.stats + 0, v0);
+        atomicAdd(P.stats + 1, v1);
+        atomicAdd(P.stats + 2, v2);
+        atomicAdd(P.stats + 3, v3);
+    }
+}
+
+template <int R, int kBlock, int kMinBlocks>
+__global__ void __launch_bounds__(kBlock, kMinBlocks) trace_kernel_const_parked(const __grid_constant__ TraceParamsConst C) {
+    __shared__ float park_mem[kParkFields * R * kBlock];
+    __shared__ uint8_t todo_mem[kBlock * R];
+    trace_body_parked<R, kBlock>(C.p, C.pairs, C.p.geom, park_mem, todo_mem);
+}
+
 // K1a: geometry in the constant bank (kernel parameter): the default for scenes of up to
 // kMaxConstSpheres spheres.  The sweep's sphere operands are uniform registers fed by LDCU; they cost
 // no register-file bandwidth, which is what bounds FFMA2 on sm_100.  No shared memory at all.
 template <int kBlock, int kMinBlocks>
 __global__ void __launch_bounds__(kBlock, kMinBlocks) trace_kernel_const(const __grid_constant__ TraceParamsConst C) {
-    trace_body(C.p, C.pairs, C.p.geom);
+    trace_body<true>(C.p, C.pairs, C.p.geom);
 }
 
 // K1b: geometry staged into shared memory by 1-D TMA bulk copies (cp.async.bulk + mbarrier): scenes
@@ -324,7 +585,7 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks) trace_kernel_smem(const __
         bulk_g2s(s_geom, P.geom, bytes, &s_bar);
     }
     mbar_wait(&s_bar, 0);
-    trace_body(P, s_pairs, s_geom);
+    trace_body<false>(P, s_pairs, s_geom);
 }
 
 // ---------------------------------------------------------------------------------------------
