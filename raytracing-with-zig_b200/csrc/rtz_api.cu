@@ -134,7 +134,11 @@ rtz::DevCamera to_dev_camera(const rtz_camera& c, uint64_t seed) {
 }
 
 // chunk size: <= 256 samples of one pixel, and enough chunks to keep every warp busy
-uint32_t pick_chunk(uint32_t spp) { return spp < 256u ? spp : 256u; }
+uint32_t pick_chunk(uint32_t spp) {
+    uint32_t cap = 256u;
+    if (const char* e = std::getenv("RTZ_CHUNK")) cap = (uint32_t)std::max(1, std::atoi(e));  // experiments
+    return spp < cap ? spp : cap;
+}
 
 template <class Kern, class Params>
 int32_t launch_trace(rtz_context* ctx, Kern kern, const Params& P, uint64_t n_chunks, int block, size_t smem) {
