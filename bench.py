@@ -45,7 +45,7 @@ WORKLOADS = {
     "smoke": (400, 10, "reference test render: final scene 400x225, 10 spp (dev only)"),
 }
 FLOP_PER_TEST = 17.0  # SURVEY.md §8d / BASELINE.md §3
-TILE = (32, 8)
+TILE = (4, 4)
 
 
 def measured_peaks():

@@ -11,7 +11,7 @@ import numpy as np
 
 from . import binding as B
 
-DEFAULT_TILE = (32, 8)  # measured: max/mean shard time 1.02 at 8 ranks (16x16: 1.067; tools/shard_balance.py)
+DEFAULT_TILE = (4, 4)  # measured on C3, max/mean shard time at 8 / 4 / 2 ranks: 1.004 / 1.001 / 1.000 (32x8: 1.023 / 1.011 / 1.009; tools/shard_balance.py)
 
 
 def tile_index_map(width: int, height: int, world: int, tile_w: int, tile_h: int):

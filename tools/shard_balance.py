@@ -7,8 +7,8 @@ sp, n = host.generate_world(0xDEADBEEF); r.upload(sp, n)
 cam = host.main_camera(1200, 500, seed=0xDEADBEEF)
 whole, st = r.render(cam); whole, st = r.render(cam)
 print("whole frame", round(st.trace_ms, 2), "ms")
-for world in (8,):
-    for tile in ((16, 16), (8, 8), (32, 8), (4, 4), (64, 4), (1200, 1)):
+for world in (8, 4, 2):
+    for tile in ((32, 8), (8, 8), (4, 4), (8, 2), (2, 2), (16, 1)):
         ms = []
         for rank in range(world):
             img, s2 = r.render(cam, pkg.rtz_shard(rank, world, tile[0], tile[1]))
