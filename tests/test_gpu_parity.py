@@ -210,6 +210,50 @@ def test_c3_full_size_properties(gpu):
     assert np.abs(ma - mc).max() < 1.0, (ma, mc)
 
 
+# ------------------------------------------------------------------ full-size properties (C4, C5)
+def test_c4_geometry_sharded_equals_whole(pkg, gpu):
+    """C4's frame (3840x2160) at a bounded spp: the 8 interleaved shards of the default 4x4 tiling, gathered and
+    de-interleaved, are the whole frame byte for byte, and their work counters add up."""
+    import torch
+    dist = __import__("importlib").import_module("raytracing-with-zig_b200.distributed")
+    tw, th = dist.DEFAULT_TILE
+    prng, sp, n = R.final_scene(0xDEADBEEF)
+    cam = R.main_camera(3840, 4, seed=0xDEADBEEF)
+    assert (cam.width, cam.height) == (3840, 2160)
+    gpu.upload(sp, n)
+    whole, st = gpu.render(cam)
+    assert st.samples == 3840 * 2160 * 4 and st.sphere_tests == st.segments * 485
+    parts, segs, samples = [], 0, 0
+    for rank in range(8):
+        part, pst = gpu.render(cam, pkg.rtz_shard(rank, 8, tw, th))
+        parts.append(part)
+        segs += pst.segments
+        samples += pst.samples
+    img = gpu.deinterleave(torch.cat(parts, 0), cam.width, cam.height, 8, tw, th)
+    assert torch.equal(img, whole)
+    assert (segs, samples) == (st.segments, st.samples)
+
+
+@pytest.mark.parametrize("n_spheres", [16, 512, 513, 4096])
+def test_c5_full_size_properties(gpu, orc, n_spheres):
+    """C5's frame (1920x1080, 64 spp) at both ends of the sweep and on both sides of the constant-bank /
+    shared-memory kernel switch (512 | 513): counters, idempotence, and a work model that grows with N."""
+    prng = orc.orc_prng_new(0xDEADBEEF)
+    buf = (R.Sphere * 4096)()
+    assert orc.orc_generate_sweep(prng, n_spheres, buf) == n_spheres
+    cam = R.main_camera(1920, 64, seed=0xDEADBEEF)
+    assert (cam.width, cam.height) == (1920, 1080)
+    gpu.upload(buf, n_spheres)
+    a, sa = gpu.render(cam)
+    b, sb = gpu.render(cam)
+    assert sa.samples == 1920 * 1080 * 64
+    assert sa.sphere_tests == sa.segments * n_spheres
+    assert np.array_equal(a.cpu().numpy(), b.cpu().numpy())
+    assert (sa.segments, sa.depth_capped, sa.absorbed) == (sb.segments, sb.depth_capped, sb.absorbed)
+    assert 2.0 < sa.segments / sa.samples < 3.0
+    assert sa.depth_capped / sa.samples <= 1e-3
+
+
 # ------------------------------------------------------------------ edge cases
 def test_edge_cases(pkg, gpu, orc):
     l = pkg.lib()
