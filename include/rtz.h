@@ -149,6 +149,18 @@ int32_t rtz_context_destroy(rtz_context* ctx);
  * src/hittable.zig:60-62, for the whole list at once). */
 int32_t rtz_scene_upload(rtz_context* ctx, const rtz_sphere* spheres, uint64_t n_spheres);
 
+/* Scene.init(seed) followed by Scene.generateWorld / generateChapter13 (src/Scene.zig:23-46, 48-134,
+ * 136-182), or BASELINE config 5's generalised final scene of exactly n_spheres spheres, generated ON THE
+ * DEVICE by one thread with the reference's exact PRNG stream (Zig std DefaultPrng = Xoshiro256++ seeded by
+ * SplitMix64, Random.float(f64)), then installed as the context's scene like rtz_scene_upload does.
+ * spheres_out (optional, host, `cap` entries) receives the f64 spheres in list order, *n_out their number,
+ * prng_state_out (optional) the four words of Scene.prng after generation.   */
+#define RTZ_SCENE_FINAL 0      /* generateWorld: ~485 spheres                                  */
+#define RTZ_SCENE_CHAPTER13 1  /* generateChapter13: 5 spheres, no random draws                */
+#define RTZ_SCENE_SWEEP 2      /* config 5: exactly n_spheres (>= 4) spheres                   */
+int32_t rtz_scene_generate(rtz_context* ctx, int32_t kind, uint64_t seed, uint64_t n_spheres,
+                           rtz_sphere* spheres_out, uint64_t cap, uint64_t* n_out, uint64_t prng_state_out[4]);
+
 /* Number of pixels (padded) in rank's compact tile buffer for this image. */
 uint64_t rtz_shard_pixels(uint64_t width, uint64_t height, const rtz_shard* shard);
 

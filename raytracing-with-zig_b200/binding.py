@@ -54,6 +54,7 @@ class rtz_scatter(C.Structure):
 
 
 RTZ_OK = 0
+SCENE_FINAL, SCENE_CHAPTER13, SCENE_SWEEP = 0, 1, 2
 ERR_NAMES = {1: "RTZ_ERR_BAD_ARG", 2: "RTZ_ERR_NO_DEVICE", 3: "RTZ_ERR_CUDA", 4: "RTZ_ERR_IO",
              5: "RTZ_ERR_TOO_MANY_SPHERES", 6: "RTZ_ERR_ARCH"}
 
@@ -67,6 +68,7 @@ SIGNATURES = {
     "rtz_context_create": (_i32, [_i32, _vp, C.POINTER(_vp)]),
     "rtz_context_destroy": (_i32, [_vp]),
     "rtz_scene_upload": (_i32, [_vp, C.POINTER(rtz_sphere), _u64]),
+    "rtz_scene_generate": (_i32, [_vp, _i32, _u64, _u64, C.POINTER(rtz_sphere), _u64, C.POINTER(_u64), C.POINTER(_u64)]),
     "rtz_shard_pixels": (_u64, [_u64, _u64, C.POINTER(rtz_shard)]),
     "rtz_render_resident": (_i32, [_vp, C.POINTER(rtz_camera), C.POINTER(rtz_shard), _vp, C.POINTER(rtz_stats)]),
     "rtz_deinterleave": (_i32, [_vp, _u64, _u64, _u32, _u32, _u32, _vp, _vp]),

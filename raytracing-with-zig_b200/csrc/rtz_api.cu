@@ -16,6 +16,7 @@
 
 #include "../../include/rtz.h"
 #include "rtz_kernels.cuh"
+#include "rtz_scene.cuh"
 
 namespace {
 
@@ -431,6 +432,44 @@ int32_t rtz_scene_upload(rtz_context* c, const rtz_sphere* sp, uint64_t n) {
     c->h_pairs = pr;  // host copy: small scenes can travel to the kernel as a __grid_constant__ parameter
     c->n_spheres = (int)n, c->n_pad = n_pad;
     return RTZ_OK;
+}
+
+int32_t rtz_scene_generate(rtz_context* c, int32_t kind, uint64_t seed, uint64_t n_spheres, rtz_sphere* out,
+                           uint64_t cap, uint64_t* n_out, uint64_t state_out[4]) {
+    if (!c || kind < RTZ_SCENE_FINAL || kind > RTZ_SCENE_SWEEP) return RTZ_ERR_BAD_ARG;
+    if (kind == RTZ_SCENE_SWEEP && (n_spheres < 4 || n_spheres > (1u << 20))) return RTZ_ERR_BAD_ARG;
+    RTZ_CUDA(cudaSetDevice(c->device));
+    // capacity of the device list: the final scene has at most 22*22 + 4 spheres, the sweep exactly n
+    const uint64_t dev_cap = kind == RTZ_SCENE_SWEEP ? n_spheres : 22 * 22 + 4;
+    rtz_sphere* d_sp = nullptr;
+    rtz::SceneGenOut* d_res = nullptr;
+    RTZ_CUDA(cudaMalloc(&d_sp, dev_cap * sizeof(rtz_sphere)));
+    if (cudaMalloc(&d_res, sizeof(rtz::SceneGenOut)) != cudaSuccess) {
+        cudaFree(d_sp);
+        return RTZ_ERR_CUDA;
+    }
+    rtz::scene_kernel<<<1, 1, 0, c->stream>>>(kind, seed, n_spheres, d_sp, dev_cap, d_res);
+    rtz::SceneGenOut res{};
+    std::vector<rtz_sphere> host;
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaMemcpyAsync(&res, d_res, sizeof res, cudaMemcpyDeviceToHost, c->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    if (e == cudaSuccess && res.count > 0 && res.count <= dev_cap) {
+        host.resize(res.count);
+        e = cudaMemcpyAsync(host.data(), d_sp, res.count * sizeof(rtz_sphere), cudaMemcpyDeviceToHost, c->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    }
+    cudaFree(d_sp), cudaFree(d_res);
+    if (e != cudaSuccess) {
+        g_last_error = cudaGetErrorString(e);
+        return RTZ_ERR_CUDA;
+    }
+    if (res.count == 0 || res.count > dev_cap) return RTZ_ERR_BAD_ARG;  // the sweep could not reach n spheres
+    if (n_out) *n_out = res.count;
+    if (state_out) std::memcpy(state_out, res.state, sizeof res.state);
+    if (out)
+        for (uint64_t i = 0; i < res.count && i < cap; ++i) out[i] = host[i];
+    return rtz_scene_upload(c, host.data(), res.count);
 }
 
 uint64_t rtz_shard_pixels(uint64_t W, uint64_t H, const rtz_shard* s) {

@@ -64,6 +64,19 @@ class Renderer:
         B.check(self.lib.rtz_scene_upload(self._ctx, ptr, n))
         self.n_spheres = n
 
+    def generate(self, kind: int, seed: int, n: int = 0):
+        """Scene.init(seed) + generateWorld / generateChapter13 / the config-5 sweep scene, generated on the
+        device with the reference's PRNG stream and installed as this renderer's scene.
+        Returns (spheres, count, prng_state): the f64 spheres in list order and Scene.prng after generation."""
+        cap = int(n) if kind == B.SCENE_SWEEP else 22 * 22 + 4
+        arr = (B.rtz_sphere * max(cap, 1))()
+        cnt = C.c_uint64(0)
+        state = (C.c_uint64 * 4)()
+        B.check(self.lib.rtz_scene_generate(self._ctx, int(kind), C.c_uint64(seed), C.c_uint64(n), arr, cap,
+                                            C.byref(cnt), state))
+        self.n_spheres = int(cnt.value)
+        return arr, int(cnt.value), [int(x) for x in state]
+
     def shard_pixels(self, width: int, height: int, shard: B.rtz_shard | None) -> int:
         return int(self.lib.rtz_shard_pixels(width, height, C.byref(shard) if shard is not None else None))
 

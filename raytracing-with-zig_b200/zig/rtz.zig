@@ -58,6 +58,11 @@ pub const rtz_stats = extern struct {
 pub extern "rtz" fn rtz_render(camera: *const rtz_camera, spheres: [*]const rtz_sphere, n_spheres: u64, rgb_out: [*]u8, stats_out: ?*rtz_stats) i32;
 pub extern "rtz" fn rtz_write_ppm(path: [*:0]const u8, width: u64, height: u64, rgb: [*]const u8) i32;
 pub extern "rtz" fn rtz_strerror(status: i32) [*:0]const u8;
+// resident API + device-side Scene.generateWorld (kind 0 final world, 1 chapter 13, 2 sweep of n spheres)
+pub const rtz_context = opaque {};
+pub extern "rtz" fn rtz_context_create(device: i32, stream: ?*anyopaque, ctx_out: *?*rtz_context) i32;
+pub extern "rtz" fn rtz_context_destroy(ctx: *rtz_context) i32;
+pub extern "rtz" fn rtz_scene_generate(ctx: *rtz_context, kind: i32, seed: u64, n_spheres: u64, spheres_out: ?[*]rtz_sphere, cap: u64, n_out: ?*u64, prng_state_out: ?*[4]u64) i32;
 pub extern "rtz" fn rtz_last_error() [*:0]const u8;
 
 pub const RenderError = error{RenderFailed};

@@ -254,6 +254,57 @@ def test_c5_full_size_properties(gpu, orc, n_spheres):
     assert sa.depth_capped / sa.samples <= 1e-3
 
 
+# ------------------------------------------------------------------ device-side scene generation
+def _same_spheres(a, b, n):
+    return bytes(a)[: n * C.sizeof(R.Sphere)] == bytes(b)[: n * C.sizeof(R.Sphere)]
+
+
+@pytest.mark.parametrize("seed", [0xDEADBEEF, 0xABADCAFE, 1, 2**64 - 1])
+def test_device_generate_world_matches_oracle(pkg, gpu, orc, seed):
+    """generateWorld on the device (Zig's Xoshiro256++ / Random.float stream restated in CUDA) gives the
+    oracle's spheres byte for byte, the 485-object KAT of src/Scene.zig:189-205, and the same PRNG state."""
+    prng = orc.orc_prng_new(seed)
+    ref = (R.Sphere * 500)()
+    n_ref = orc.orc_generate_world(prng, ref, 500)
+    st_ref = (C.c_uint64 * 4)()
+    orc.orc_prng_state(prng, st_ref)
+    sp, n, state = gpu.generate(pkg.binding.SCENE_FINAL, seed)
+    assert n == n_ref
+    if seed in (0xDEADBEEF, 0xABADCAFE):
+        assert n == 485
+    assert _same_spheres(sp, ref, n)
+    assert state == [int(x) for x in st_ref]
+    # and it is installed: rendering it equals rendering the uploaded oracle scene
+    cam = R.main_camera(64, 3, seed=5)
+    a, sa = gpu.render(cam)
+    gpu.upload(ref, n_ref)
+    b, sb = gpu.render(cam)
+    assert np.array_equal(a.cpu().numpy(), b.cpu().numpy()) and sa.segments == sb.segments
+
+
+@pytest.mark.parametrize("n_spheres", [4, 16, 485, 512, 1024, 4096])
+def test_device_generate_sweep_matches_oracle(pkg, gpu, orc, n_spheres):
+    prng = orc.orc_prng_new(0xDEADBEEF)
+    ref = (R.Sphere * n_spheres)()
+    assert orc.orc_generate_sweep(prng, n_spheres, ref) == n_spheres
+    st_ref = (C.c_uint64 * 4)()
+    orc.orc_prng_state(prng, st_ref)
+    sp, n, state = gpu.generate(pkg.binding.SCENE_SWEEP, 0xDEADBEEF, n_spheres)
+    assert n == n_spheres and _same_spheres(sp, ref, n)
+    assert state == [int(x) for x in st_ref]
+
+
+def test_device_generate_chapter13_and_bad_args(pkg, gpu, orc):
+    ref = (R.Sphere * 5)()
+    assert orc.orc_generate_chapter13(ref, 5) == 5
+    sp, n, state = gpu.generate(pkg.binding.SCENE_CHAPTER13, 7)
+    assert n == 5 and _same_spheres(sp, ref, 5)
+    with pytest.raises(pkg.binding.RtzError):
+        gpu.generate(pkg.binding.SCENE_SWEEP, 1, 3)      # fewer than the four fixed spheres
+    with pytest.raises(pkg.binding.RtzError):
+        gpu.generate(9, 1)                                # unknown kind
+
+
 # ------------------------------------------------------------------ edge cases
 def test_edge_cases(pkg, gpu, orc):
     l = pkg.lib()
