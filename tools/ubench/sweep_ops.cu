@@ -187,7 +187,7 @@ int main() {
     static ConstGeoT CT;
     memcpy(CT.geo, g.data(), 512 * 16);
     const int sms = p.multiProcessorCount;
-    for (int tps : {768, 512}) {
+    for (int tps : {2048, 1536, 1024, 768}) {
         printf("-- up to %d threads per SM\n", tps);
         runt<2, 0>("V0 baseline (8 packed + 2 SHF per pair)", CT, sink, sms, tps, 8);
         runt<2, 1>("V1 no disc op (7 packed)", CT, sink, sms, tps, 7);
