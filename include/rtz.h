@@ -37,7 +37,8 @@ extern "C" {
 #define RTZ_ERR_NO_DEVICE 2    /* no CUDA device / driver: the product has no CPU path        */
 #define RTZ_ERR_CUDA 3         /* a CUDA runtime call or a kernel failed; see rtz_last_error  */
 #define RTZ_ERR_IO 4           /* rtz_write_ppm could not create / write the file             */
-#define RTZ_ERR_TOO_MANY_SPHERES 5 /* scene does not fit the shared-memory staging buffer     */
+#define RTZ_ERR_TOO_MANY_SPHERES 5 /* more than 2^20 spheres (larger scenes than shared memory   */
+                                   /* holds are swept from global memory, they are not an error) */
 #define RTZ_ERR_ARCH 6         /* device is not sm_100 (the library ships sm_100a code only)  */
 
 /* ---- material tags: reference src/material.zig:113-117 (MaterialType) ------------ */

@@ -178,10 +178,7 @@ int32_t render_path(rtz_context* ctx, const rtz_camera* cam, const rtz::ShardGeo
     P.stats = ctx->counters.p + 1;
     const bool use_const = ctx->n_pad <= rtz::kMaxConstSpheres && ctx->geo_const;
     const size_t smem = use_const ? 0 : (size_t)ctx->n_pad * 32;  // pair layout + per-lane rows
-    if (smem + 1024 > ctx->smem_optin) {
-        g_last_error = "scene does not fit in shared memory";
-        return RTZ_ERR_TOO_MANY_SPHERES;
-    }
+    const bool use_global = !use_const && smem + 1024 > ctx->smem_optin;  // too large to stage: read it from L1/L2
     RTZ_CUDA(cudaEventRecord(ctx->ev[0], ctx->stream));
     RTZ_CUDA(cudaMemsetAsync(ctx->accum.p, 0, 3 * n_local_pixels * sizeof(unsigned long long), ctx->stream));
     RTZ_CUDA(cudaMemsetAsync(ctx->counters.p, 0, 8 * sizeof(unsigned long long), ctx->stream));
@@ -203,6 +200,8 @@ int32_t render_path(rtz_context* ctx, const rtz_camera* cam, const rtz::ShardGeo
             rc = launch_trace(ctx, rtz::trace_kernel_const<128, 5>, C, P.n_chunks, 128, 0);
         else
             rc = launch_trace(ctx, rtz::trace_kernel_const<128, 6>, C, P.n_chunks, 128, 0);
+    } else if (use_global) {
+        rc = launch_trace(ctx, rtz::trace_kernel_global<128, 5>, P, P.n_chunks, 128, 0);
     } else {
         // Launch shape: the one that keeps most warps resident for this scene's shared-memory
         // footprint.  <128,5> (94 registers, 20 warps/SM) is the measured best while five CTAs fit;

@@ -588,6 +588,14 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks) trace_kernel_smem(const __
     trace_body<false>(P, s_pairs, s_geom);
 }
 
+// K1c: geometry read from global memory (L1 / L2, warp-uniform addresses): scenes whose 32 B per sphere do
+// not fit the shared memory of an SM (more than ~7 200 spheres).  The reference's HittableList has no size
+// limit (src/hittable.zig:43-62), so neither has the drop-in; the sweep just loses its staging.
+template <int kBlock, int kMinBlocks>
+__global__ void __launch_bounds__(kBlock, kMinBlocks) trace_kernel_global(const __grid_constant__ TraceParams P) {
+    trace_body<false>(P, P.pairs, P.geom);
+}
+
 // ---------------------------------------------------------------------------------------------
 // K3: resolve.  pixelColor * pixelSamplesScale (src/camera.zig:137), then Color.toRgb
 // (src/color.zig:63-80): sqrt if > 0, clamp [0, .999], trunc(256 x).  f64 like the reference
