@@ -161,7 +161,7 @@ int32_t launch_trace(rtz_context* ctx, Kern kern, const Params& P, uint64_t n_ch
 
 int32_t render_path(rtz_context* ctx, const rtz_camera* cam, const rtz::ShardGeom& sg, uint8_t* d_rgb,
                     double* d_linear, rtz_stats* st, uint64_t seed) {
-    if (ctx->n_spheres <= 0) return RTZ_ERR_BAD_ARG;
+    if (ctx->n_spheres < 0) return RTZ_ERR_BAD_ARG;  // an empty world is a valid HittableList: every ray sees the sky
     const uint64_t n_local_pixels = (uint64_t)sg.n_local_tiles * sg.tile_pixels;
     if (n_local_pixels > 0xFFFFFFFFull) return RTZ_ERR_BAD_ARG;
     RTZ_CUDA(ctx->accum.reserve(3 * n_local_pixels));

@@ -340,6 +340,12 @@ def test_edge_cases(pkg, gpu, orc):
     rgb, st = pkg.render_host(cam, sp, 3)
     mrgb, _, _ = _mirror(orc, cam, sp, 3, 11)
     assert np.array_equal(rgb.reshape(-1, 3), mrgb)
+    # empty world (HittableList.clear, src/hittable.zig:56-58): every ray misses, one segment per sample, sky
+    cam = R.build_camera(48, 16.0 / 9.0, (0, 0, 0), (0, 0, -1), 90, spp=2, seed=4)
+    rgb, st = pkg.render_host(cam, sp, 0)
+    mrgb, _, mst = _mirror(orc, cam, sp, 0, 4)
+    assert st.segments == st.samples == mst.segments and st.sphere_tests == 0
+    assert np.array_equal(rgb.reshape(-1, 3), mrgb) and rgb.min() > 100
     # bad arguments fail loudly
     st = pkg.rtz_stats()
     bad = pkg.rtz_camera()
