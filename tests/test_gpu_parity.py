@@ -157,6 +157,62 @@ def test_seed_changes_image_and_is_reported(gpu):
     assert sc.seed_used != sd.seed_used
 
 
+# ------------------------------------------------------------------ stochastic: GPU vs the f64 reference restatement
+def _rmse(a, b):
+    return float(np.sqrt(np.mean((a.astype(np.float64) - b.astype(np.float64)) ** 2)))
+
+
+@pytest.mark.parametrize("preset", list(CH13_CAMERAS))
+def test_c2_config_rmse_vs_f64_reference(gpu, orc, preset):
+    """BASELINE config 2 as stated: four-material scene, 400x225, 100 spp, depth 50, the GPU image against the
+    CPU restatement of the reference (f64, per-sample Philox streams).  Tolerance: RMSE of the 8-bit image
+    <= 1.25 x the reference's own seed-to-seed RMSE (its Monte-Carlo noise floor at 100 spp, ~5-6 levels =
+    PSNR ~32-34 dB), |mean bias| <= 0.25 level per channel, segments per sample within 1 %."""
+    sp, n = R.chapter13_scene()
+    cam = R.build_camera(400, 16.0 / 9.0, spp=100, seed=0xDEADBEEF, **CH13_CAMERAS[preset])
+    assert (cam.width, cam.height, cam.samples_per_pixel, cam.bounce_max) == (400, 225, 100, 50)
+    gpu.upload(sp, n)
+    img, st = gpu.render(cam)
+    g = img.cpu().numpy()
+    threads = max(1, orc.orc_hardware_threads())
+    a = np.zeros((225, 400, 3), np.uint8)
+    b = np.zeros_like(a)
+    ast = R.Stats()
+    u8 = lambda x: x.ctypes.data_as(C.POINTER(C.c_uint8))
+    assert orc.orc_render_philox64(C.byref(cam), sp, n, 1, threads, u8(a), None, C.byref(ast)) == 0
+    assert orc.orc_render_philox64(C.byref(cam), sp, n, 2, threads, u8(b), None, None) == 0
+    floor = _rmse(a, b)
+    err = _rmse(g, a)
+    bias = np.abs((g.astype(np.float64) - a.astype(np.float64)).mean(axis=(0, 1)))
+    assert err <= 1.25 * floor, (err, floor)
+    assert bias.max() <= 0.25, bias
+    assert abs(st.segments / st.samples - ast.segments / ast.samples) <= 0.01 * ast.segments / ast.samples
+
+
+def test_final_scene_rmse_vs_f64_reference(gpu, orc):
+    """The Book-1 final scene (C3 / C4's scene and camera) at 400x225, 100 spp against the f64 restatement of
+    the reference: same tolerances as config 2 (RMSE <= 1.25 x the reference's seed-to-seed RMSE, |bias| <= 0.25
+    level, segments per sample within 1 %, depth-capped samples <= 0.05 %)."""
+    prng, sp, n = R.final_scene(0xDEADBEEF)
+    cam = R.main_camera(400, 100, seed=0xDEADBEEF)
+    gpu.upload(sp, n)
+    img, st = gpu.render(cam)
+    g = img.cpu().numpy()
+    threads = max(1, orc.orc_hardware_threads())
+    a = np.zeros((225, 400, 3), np.uint8)
+    b = np.zeros_like(a)
+    ast = R.Stats()
+    u8 = lambda x: x.ctypes.data_as(C.POINTER(C.c_uint8))
+    assert orc.orc_render_philox64(C.byref(cam), sp, n, 1, threads, u8(a), None, C.byref(ast)) == 0
+    assert orc.orc_render_philox64(C.byref(cam), sp, n, 2, threads, u8(b), None, None) == 0
+    floor, err = _rmse(a, b), _rmse(g, a)
+    bias = np.abs((g.astype(np.float64) - a.astype(np.float64)).mean(axis=(0, 1)))
+    assert err <= 1.25 * floor, (err, floor)
+    assert bias.max() <= 0.25, bias
+    assert abs(st.segments / st.samples - ast.segments / ast.samples) <= 0.01 * ast.segments / ast.samples
+    assert st.depth_capped / st.samples <= 5e-4
+
+
 # ------------------------------------------------------------------ sharding: any world == 1 GPU
 @pytest.mark.parametrize("world,tile", [(2, (16, 16)), (3, (32, 8)), (8, (16, 16)), (4, (7, 5))])
 def test_interleaved_tiles_equal_whole_frame(pkg, gpu, orc, world, tile):
