@@ -221,6 +221,13 @@ int32_t rtz_probe_uniform(uint64_t seed, uint32_t pixel, uint32_t sample, uint32
                           uint64_t n, float* out);
 
 /* ---- diagnostics ------------------------------------------------------------------ */
+/* Camera.getRay(i, j) for sample `sample` of pixel (i, j) (src/camera.zig:187-215: sampleSquare jitter,
+ * defocusDiskSample origin), evaluated by the DEVICE code of the render kernel: n rays for samples
+ * sample0 .. sample0+n-1.  origin_out / dir_out receive 3 floats per ray (dir is the UNIT direction),
+ * len_out (optional) the length of the un-normalised `pixelSample - origin` the reference stores. */
+int32_t rtz_probe_camera_ray(const rtz_camera* camera, uint64_t i, uint64_t j, uint64_t sample0, uint64_t n,
+                             float* origin_out, float* dir_out, float* len_out);
+
 const char* rtz_strerror(int32_t status);
 const char* rtz_last_error(void);   /* detail of the last RTZ_ERR_CUDA on this thread        */
 int32_t rtz_abi_version(void);

@@ -335,6 +335,27 @@ int orc_render_mirror(const rtz_camera* cam, const rtz_sphere* sp, uint64_t n, u
     return RTZ_OK;
 }
 
+// Camera.getRay as the device evaluates it (mirror of rtz_probe_camera_ray): n rays of pixel (i, j)
+void orc_mirror_camera_ray(const rtz_camera* cam, uint64_t seed, uint32_t i, uint32_t j, uint32_t sample0, uint32_t n,
+                           float* o, float* d, float* len) {
+    MCamera c;
+    c.p0 = f3(cam->pixel0), c.du = f3(cam->du), c.dv = f3(cam->dv), c.c = f3(cam->center);
+    c.uu = f3(cam->defocus_disk_u), c.vv = f3(cam->defocus_disk_v);
+    c.tmin = (float)cam->t_min, c.tmax = (float)cam->t_max;
+    c.defocus = cam->defocus_angle > 0;
+    c.W = (uint32_t)cam->width, c.H = (uint32_t)cam->height;
+    c.spp = (uint32_t)cam->samples_per_pixel, c.bounce_max = (uint32_t)cam->bounce_max;
+    c.k0 = (uint32_t)seed, c.k1 = (uint32_t)(seed >> 32);
+    for (uint32_t k = 0; k < n; ++k) {
+        Rng g{{c.k0, c.k1}, j * c.W + i, sample0 + k};
+        Path p;
+        cameraRay(c, g, i, j, p);
+        o[3 * k] = p.o.x, o[3 * k + 1] = p.o.y, o[3 * k + 2] = p.o.z;
+        d[3 * k] = p.d.x, d[3 * k + 1] = p.d.y, d[3 * k + 2] = p.d.z;
+        if (len) len[k] = p.len;
+    }
+}
+
 // one-ray mirrors of the device probes
 void orc_mirror_uniform(uint64_t seed, uint32_t pixel, uint32_t sample, uint32_t bounce, uint64_t n, float* out) {
     Rng g{{(uint32_t)seed, (uint32_t)(seed >> 32)}, pixel, sample};

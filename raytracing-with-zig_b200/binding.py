@@ -77,6 +77,7 @@ SIGNATURES = {
                                  C.POINTER(rtz_scatter)]),
     "rtz_probe_to_rgb": (_i32, [_f64p, _u64, _u8p]),
     "rtz_probe_uniform": (_i32, [_u64, _u32, _u32, _u32, _u64, _f32p]),
+    "rtz_probe_camera_ray": (_i32, [C.POINTER(rtz_camera), _u64, _u64, _u64, _u64, _f32p, _f32p, _f32p]),
     "rtz_strerror": (C.c_char_p, [_i32]),
     "rtz_last_error": (C.c_char_p, []),
     "rtz_abi_version": (_i32, []),

@@ -646,6 +646,30 @@ int32_t rtz_probe_to_rgb(const double* lin, uint64_t n, uint8_t* rgb_out) {
     return RTZ_OK;
 }
 
+int32_t rtz_probe_camera_ray(const rtz_camera* cam, uint64_t i, uint64_t j, uint64_t sample0, uint64_t n, float* o_out,
+                             float* d_out, float* len_out) {
+    if (!o_out || !d_out || !n || n > (1u << 24)) return RTZ_ERR_BAD_ARG;
+    int32_t rc = check_camera(cam);
+    if (rc != RTZ_OK) return rc;
+    if (i >= cam->width || j >= cam->height) return RTZ_ERR_BAD_ARG;
+    ScopedCtx sc;
+    rc = rtz_context_create(-1, nullptr, &sc.c);
+    if (rc != RTZ_OK) return rc;
+    const rtz::DevCamera dc = to_dev_camera(*cam, cam->has_seed ? cam->seed : os_seed());
+    float* buf;
+    RTZ_CUDA(cudaMalloc(&buf, n * 7 * sizeof(float)));
+    float *d_o = buf, *d_d = buf + 3 * n, *d_l = buf + 6 * n;
+    rtz::probe_camera_ray_kernel<<<(unsigned)((n + 127) / 128), 128, 0, sc.c->stream>>>(
+        dc, (uint32_t)i, (uint32_t)j, (uint32_t)sample0, (uint32_t)n, d_o, d_d, d_l);
+    cudaError_t e = cudaMemcpyAsync(o_out, d_o, 3 * n * sizeof(float), cudaMemcpyDeviceToHost, sc.c->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_out, d_d, 3 * n * sizeof(float), cudaMemcpyDeviceToHost, sc.c->stream);
+    if (e == cudaSuccess && len_out) e = cudaMemcpyAsync(len_out, d_l, n * sizeof(float), cudaMemcpyDeviceToHost, sc.c->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(sc.c->stream);
+    cudaFree(buf);
+    RTZ_CUDA(e);
+    return RTZ_OK;
+}
+
 int32_t rtz_probe_uniform(uint64_t seed, uint32_t pixel, uint32_t sample, uint32_t bounce, uint64_t n, float* out) {
     if (!out || !n) return RTZ_ERR_BAD_ARG;
     ScopedCtx sc;

@@ -762,6 +762,18 @@ __global__ void probe_scatter_kernel(DevCamera cam, const float4* geom, const fl
     out->att[0] = p.tr, out->att[1] = p.tg, out->att[2] = p.tb;
 }
 
+__global__ void probe_camera_ray_kernel(DevCamera cam, uint32_t i, uint32_t j, uint32_t sample0, uint32_t n, float* o,
+                                        float* d, float* len) {
+    const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    const RngKey key{cam.key0, cam.key1, j * cam.width + i, sample0 + k};
+    Path p;
+    camera_ray(cam, key, i, j, p);
+    o[3 * k + 0] = p.ox, o[3 * k + 1] = p.oy, o[3 * k + 2] = p.oz;
+    d[3 * k + 0] = p.dx, d[3 * k + 1] = p.dy, d[3 * k + 2] = p.dz;
+    if (len) len[k] = p.len;
+}
+
 __global__ void probe_to_rgb_kernel(const double* lin, uint64_t n3, uint8_t* out) {
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n3) out[i] = to_byte(lin[i]);

@@ -197,6 +197,10 @@ def oracle():
     if hasattr(lib, "orc_render_mirror"):
         lib.orc_render_mirror.restype = i32
         lib.orc_render_mirror.argtypes = [P(Camera), P(Sphere), u64, u64, i32, P(Shard), P(C.c_uint8), P(f64), P(Stats)]
+    if hasattr(lib, "orc_mirror_camera_ray"):
+        lib.orc_mirror_camera_ray.restype = None
+        lib.orc_mirror_camera_ray.argtypes = [P(Camera), u64, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32,
+                                              P(C.c_float), P(C.c_float), P(C.c_float)]
     _oracle = lib
     return lib
 

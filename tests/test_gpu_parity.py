@@ -491,6 +491,43 @@ def test_probe_scatter_kats(pkg, orc):
     assert len(seen) > 8
 
 
+def test_probe_camera_ray_kats(pkg, orc):
+    """reference src/camera.zig:539-567 (Camera.sampleSquare, Camera.defocusDiskSample) and :187-200 (getRay), on the
+    device: the jitter stays inside the pixel's square, the origin inside the defocus disk, and every float equals
+    the mirror's."""
+    l = pkg.lib()
+    F = C.POINTER(C.c_float)
+    n = 4096
+    for defocus, focus in ((0.0, 10.0), (10.0, 3.4)):
+        cam = R.build_camera(400, 1.0, (0, 0, 0), (0, 0, -1), 90, defocus=defocus, viewport_focus=focus, focus=focus,
+                             spp=1, seed=0xDEADBEEF)
+        i, j = 123, 77
+        o = np.zeros((n, 3), np.float32); d = np.zeros((n, 3), np.float32); ln = np.zeros(n, np.float32)
+        pcam = C.cast(C.byref(cam), C.POINTER(pkg.rtz_camera))
+        assert l.rtz_probe_camera_ray(pcam, i, j, 5, n, o.ctypes.data_as(F), d.ctypes.data_as(F), ln.ctypes.data_as(F)) == 0
+        mo = np.zeros_like(o); md = np.zeros_like(d); ml = np.zeros_like(ln)
+        orc.orc_mirror_camera_ray(C.byref(cam), 0xDEADBEEF, i, j, 5, n, mo.ctypes.data_as(F), md.ctypes.data_as(F), ml.ctypes.data_as(F))
+        assert np.array_equal(o, mo) and np.array_equal(d, md) and np.array_equal(ln, ml)
+        assert np.allclose(np.linalg.norm(d.astype(np.float64), axis=1), 1.0, atol=1e-6)
+        # sampleSquare: pixelSample = pixel0 + du*(i+ox) + dv*(j+oy) with ox, oy in [-0.5, 0.5]  (:189, :203-209)
+        p0, du, dv = np.array(cam.pixel0[:]), np.array(cam.du[:]), np.array(cam.dv[:])
+        ps = o.astype(np.float64) + d.astype(np.float64) * ln[:, None]
+        rel = ps - p0
+        ox = rel @ du / (du @ du) - i
+        oy = rel @ dv / (dv @ dv) - j
+        assert (np.abs(ox) <= 0.5 + 1e-4).all() and (np.abs(oy) <= 0.5 + 1e-4).all()
+        assert ox.std() > 0.25 and oy.std() > 0.25          # it is a jitter, not a constant
+        # defocusDiskSample: origin = center + a*diskU + b*diskV with a^2 + b^2 < 1  (:212-215); the centre itself otherwise
+        c = np.array(cam.center[:]); uu = np.array(cam.defocus_disk_u[:]); vv = np.array(cam.defocus_disk_v[:])
+        if defocus > 0:
+            a = (o - c) @ uu / (uu @ uu); b = (o - c) @ vv / (vv @ vv)
+            assert (a * a + b * b < 1.0 + 1e-4).all() and a.std() > 0.3 and b.std() > 0.3
+        else:
+            assert np.array_equal(o, np.tile(c.astype(np.float32), (n, 1)))
+    bad = pkg.rtz_camera()
+    assert l.rtz_probe_camera_ray(C.byref(bad), 0, 0, 0, 1, o.ctypes.data_as(F), d.ctypes.data_as(F), None) == 1
+
+
 def test_probe_to_rgb_kats(pkg, orc):
     """reference src/color.zig:131-135,157-172."""
     l = pkg.lib()
