@@ -13,25 +13,23 @@ tmp = tempfile.mkdtemp()
 subprocess.run(["cuobjdump", "-xelf", "all", os.path.abspath(so)], cwd=tmp, capture_output=True)
 cubin = glob.glob(tmp + "/*.cubin")[0]
 dis = subprocess.run(["nvdisasm", "-gi", cubin], capture_output=True, text=True).stdout.splitlines()
-addr2chain, chain, inside = {}, [], False
+addr2chain, chain, inside, fresh = {}, [], False, True
 for ln in dis:
     if ln.startswith("//---") and ".text." in ln:
-        inside = kname in ln
-        chain = []
+        inside, chain, fresh = kname in ln, [], True
         continue
     if not inside:
         continue
     m = re.search(r'//## File "([^"]+)", line (\d+)', ln)
-    if m:
-        if getattr(sys.modules[__name__], "_fresh", True):
-            chain = []
+    if m:  # consecutive "//## File" lines form one chain: innermost inlined frame first, kernel frame last
+        if fresh:
+            chain, fresh = [], False
         chain.append((os.path.basename(m.group(1)), int(m.group(2))))
-        _fresh = False
         continue
     m = re.match(r"\s+/\*([0-9a-f]+)\*/\s+(.*);", ln)
-    if m:
+    if m:  # an instruction: it belongs to the chain above it (or to the previous instruction's chain)
         addr2chain[int(m.group(1), 16)] = list(chain)
-        _fresh = True
+        fresh = True
 src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(src)))
 hdr, data = rows[1], rows[2:]
