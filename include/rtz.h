@@ -61,6 +61,10 @@ extern "C" {
 #define RTZ_MODE_LEGACY_SKY 1     /* chapter4: sky gradient only                              */
 #define RTZ_MODE_LEGACY_FLAT 2    /* chapter5: any hit -> flat red (1,0,0), else sky          */
 #define RTZ_MODE_LEGACY_NORMAL 3  /* chapter6: closest hit -> 0.5*(normal+1), else sky        */
+#define RTZ_MODE_PATH_BVH 4       /* EXTENSION, not in the reference: RTZ_MODE_PATH with the   */
+                                  /* closest hit found through a BVH over the spheres instead  */
+                                  /* of the brute-force list; the image is bit-identical,      */
+                                  /* rtz_stats.sphere_tests counts the tests actually made     */
 
 /* One sphere with its material inlined.
  * reference: Sphere{center,radius,mat} src/sphere.zig:13-17; Material union

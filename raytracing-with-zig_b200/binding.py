@@ -55,6 +55,7 @@ class rtz_scatter(C.Structure):
 
 RTZ_OK = 0
 SCENE_FINAL, SCENE_CHAPTER13, SCENE_SWEEP = 0, 1, 2
+MODE_PATH, MODE_PATH_BVH = 0, 4   # MODE_PATH_BVH: extension, same image through a BVH (include/rtz.h)
 ERR_NAMES = {1: "RTZ_ERR_BAD_ARG", 2: "RTZ_ERR_NO_DEVICE", 3: "RTZ_ERR_CUDA", 4: "RTZ_ERR_IO",
              5: "RTZ_ERR_TOO_MANY_SPHERES", 6: "RTZ_ERR_ARCH"}
 

@@ -16,6 +16,7 @@
 
 #include "../../include/rtz.h"
 #include "rtz_kernels.cuh"
+#include "rtz_bvh.cuh"
 #include "rtz_scene.cuh"
 
 namespace {
@@ -81,6 +82,10 @@ struct rtz_context {
     DevBuf<float4> geom, pairs, aux, albedo;
     DevBuf<rtz::DSphere> dspheres;
     std::vector<float4> h_pairs;
+    // RTZ_MODE_PATH_BVH (extension): hierarchy over the same FP32 spheres
+    DevBuf<rtz::BvhNode> bvh_nodes;
+    DevBuf<int> bvh_order;
+    DevBuf<float> bvh_wexp;
     int n_spheres = 0, n_pad = 0;
     // frame state
     DevBuf<unsigned long long> accum;
@@ -110,9 +115,9 @@ int32_t shard_geom(uint64_t W, uint64_t H, const rtz_shard* s, rtz::ShardGeom& g
 int32_t check_camera(const rtz_camera* c) {
     if (!c || c->width == 0 || c->height == 0) return RTZ_ERR_BAD_ARG;
     if (c->width * c->height > 0xFFFFFFFFull) return RTZ_ERR_BAD_ARG;
-    if (c->mode < RTZ_MODE_PATH || c->mode > RTZ_MODE_LEGACY_NORMAL) return RTZ_ERR_BAD_ARG;
+    if (c->mode < RTZ_MODE_PATH || c->mode > RTZ_MODE_PATH_BVH) return RTZ_ERR_BAD_ARG;
     if (c->samples_per_pixel == 0 || c->samples_per_pixel > 0x7FFFFFFFull) return RTZ_ERR_BAD_ARG;
-    if (c->mode != RTZ_MODE_PATH && c->samples_per_pixel != 1) return RTZ_ERR_BAD_ARG;
+    if (c->mode != RTZ_MODE_PATH && c->mode != RTZ_MODE_PATH_BVH && c->samples_per_pixel != 1) return RTZ_ERR_BAD_ARG;
     if (c->bounce_max > 0xFFFFFFFFull) return RTZ_ERR_BAD_ARG;
     return RTZ_OK;
 }
@@ -187,6 +192,9 @@ int32_t render_path(rtz_context* ctx, const rtz_camera* cam, const rtz::ShardGeo
     if (P.cam.bounce_max == 0) {
         // `while (bounces < bounceMax)` never runs (src/camera.zig:153): every sample is black and no
         // world.hit is made.  Nothing to trace; the zeroed sums resolve to zeros.
+    } else if (cam->mode == RTZ_MODE_PATH_BVH) {
+        rtz::BvhParams B{P, ctx->bvh_nodes.p, ctx->bvh_order.p, ctx->bvh_wexp.p};
+        rc = launch_trace(ctx, rtz::trace_kernel_bvh<128, 8>, B, P.n_chunks, 128, 0);
     } else if (use_const) {
         static thread_local rtz::TraceParamsConst C;  // 8 KiB: keep it off the stack
         C.p = P;
@@ -248,7 +256,7 @@ int32_t render_path(rtz_context* ctx, const rtz_camera* cam, const rtz::ShardGeo
             st->samples = px * cam->samples_per_pixel;
         }
         st->depth_capped = ctx->h_counters[3], st->absorbed = ctx->h_counters[4];
-        st->sphere_tests = st->segments * (uint64_t)ctx->n_spheres;
+        st->sphere_tests = cam->mode == RTZ_MODE_PATH_BVH ? ctx->h_counters[5] : st->segments * (uint64_t)ctx->n_spheres;
         st->kernel_launches = P.cam.bounce_max == 0 ? 1 : 2;
         float ms = 0;
         cudaEventElapsedTime(&ms, ctx->ev[1], ctx->ev[2]), st->trace_ms = ms;
@@ -373,6 +381,7 @@ int32_t rtz_context_destroy(rtz_context* c) {
     if (c->stream) cudaStreamSynchronize(c->stream);
     c->geom.release(), c->pairs.release(), c->aux.release(), c->albedo.release(), c->dspheres.release();
     c->accum.release(), c->counters.release(), c->rgb.release(), c->linear.release();
+    c->bvh_nodes.release(), c->bvh_order.release(), c->bvh_wexp.release();
     for (auto& e : c->ev)
         if (e) cudaEventDestroy(e);
     if (c->h_counters) cudaFreeHost(c->h_counters);
@@ -380,6 +389,67 @@ int32_t rtz_context_destroy(rtz_context* c) {
     delete c;
     return RTZ_OK;
 }
+
+namespace {
+// Median-split BVH over the FP32 spheres {cx, cy, cz, -r^2} (RTZ_MODE_PATH_BVH).  Boxes are padded well beyond
+// the rounding of the slab test and of the hit point, so the traversal is conservative.
+struct BvhBuilder {
+    const std::vector<float4>& g;
+    std::vector<rtz::BvhNode> nodes;
+    std::vector<int> order;
+    explicit BvhBuilder(const std::vector<float4>& geom, int n) : g(geom), order(n) {
+        for (int i = 0; i < n; ++i) order[i] = i;
+    }
+    void bounds(int first, int cnt, float lo[3], float hi[3]) const {
+        for (int a = 0; a < 3; ++a) lo[a] = INFINITY, hi[a] = -INFINITY;
+        for (int q = first; q < first + cnt; ++q) {
+            const float4 s = g[order[q]];
+            const float c[3] = {s.x, s.y, s.z};
+            const float r = std::sqrt(-s.w);
+            const float pad = 1e-4f * (1.0f + r + std::fabs(s.x) + std::fabs(s.y) + std::fabs(s.z));
+            for (int a = 0; a < 3; ++a) lo[a] = std::min(lo[a], c[a] - r - pad), hi[a] = std::max(hi[a], c[a] + r + pad);
+        }
+    }
+    // returns the child reference of the range: leaf code (< 0) or the index of a new inner node (>= 0)
+    int build(int first, int cnt) {
+        if (cnt <= 4) return -1 - (first * 8 + cnt);
+        float clo[3] = {INFINITY, INFINITY, INFINITY}, chi[3] = {-INFINITY, -INFINITY, -INFINITY};
+        for (int q = first; q < first + cnt; ++q) {
+            const float4 s = g[order[q]];
+            const float c[3] = {s.x, s.y, s.z};
+            for (int a = 0; a < 3; ++a) clo[a] = std::min(clo[a], c[a]), chi[a] = std::max(chi[a], c[a]);
+        }
+        int axis = 0;
+        for (int a = 1; a < 3; ++a)
+            if (chi[a] - clo[a] > chi[axis] - clo[axis]) axis = a;
+        const int half = cnt / 2;
+        std::nth_element(order.begin() + first, order.begin() + first + half, order.begin() + first + cnt, [&](int x, int y) {
+            const float cx = axis == 0 ? g[x].x : axis == 1 ? g[x].y : g[x].z;
+            const float cy = axis == 0 ? g[y].x : axis == 1 ? g[y].y : g[y].z;
+            return cx < cy || (cx == cy && x < y);
+        });
+        const int me = (int)nodes.size();
+        nodes.emplace_back();
+        const int c0 = build(first, half), c1 = build(first + half, cnt - half);
+        rtz::BvhNode& nd = nodes[me];
+        bounds(first, half, nd.lo0, nd.hi0);
+        bounds(first + half, cnt - half, nd.lo1, nd.hi1);
+        nd.child0 = c0, nd.child1 = c1, nd.pad0 = nd.pad1 = 0;
+        return me;
+    }
+    void run() {
+        const int n = (int)order.size();
+        nodes.reserve(n / 2 + 2);
+        const int root = n > 0 ? build(0, n) : rtz::kBvhEmpty;
+        if (root != 0) {  // fewer than five spheres (or none): a root whose first child is the only leaf
+            rtz::BvhNode nd{};
+            if (n > 0) bounds(0, n, nd.lo0, nd.hi0);
+            nd.child0 = root, nd.child1 = rtz::kBvhEmpty;
+            nodes.insert(nodes.begin(), nd);
+        }
+    }
+};
+}  // namespace
 
 int32_t rtz_scene_upload(rtz_context* c, const rtz_sphere* sp, uint64_t n) {
     if (!c || (!sp && n) || n > (1u << 20)) return RTZ_ERR_BAD_ARG;
@@ -427,6 +497,16 @@ int32_t rtz_scene_upload(rtz_context* c, const rtz_sphere* sp, uint64_t n) {
     RTZ_CUDA(c->dspheres.reserve(ds.size()));
     RTZ_CUDA(cudaMemcpyAsync(c->dspheres.p, ds.data(), ds.size() * sizeof(rtz::DSphere), cudaMemcpyHostToDevice,
                              c->stream));
+    BvhBuilder bvh(g, (int)n);
+    bvh.run();
+    RTZ_CUDA(c->bvh_nodes.reserve(bvh.nodes.size()));
+    RTZ_CUDA(c->bvh_order.reserve(std::max<size_t>(1, bvh.order.size())));
+    RTZ_CUDA(c->bvh_wexp.reserve(std::max<size_t>(1, (size_t)n)));
+    RTZ_CUDA(cudaMemcpyAsync(c->bvh_nodes.p, bvh.nodes.data(), bvh.nodes.size() * sizeof(rtz::BvhNode), cudaMemcpyHostToDevice, c->stream));
+    if (n) {
+        RTZ_CUDA(cudaMemcpyAsync(c->bvh_order.p, bvh.order.data(), n * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+        RTZ_CUDA(cudaMemcpyAsync(c->bvh_wexp.p, w.data(), n * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+    }
     RTZ_CUDA(cudaStreamSynchronize(c->stream));  // the staging vectors die here
     c->h_pairs = pr;  // host copy: small scenes can travel to the kernel as a __grid_constant__ parameter
     c->n_spheres = (int)n, c->n_pad = n_pad;
@@ -483,7 +563,7 @@ static int32_t render_resident_impl(rtz_context* c, const rtz_camera* cam, const
     int32_t rc = check_camera(cam);
     if (rc != RTZ_OK) return rc;
     RTZ_CUDA(cudaSetDevice(c->device));
-    if (cam->mode != RTZ_MODE_PATH) {
+    if (cam->mode != RTZ_MODE_PATH && cam->mode != RTZ_MODE_PATH_BVH) {
         if (shard && shard->world != 1) return RTZ_ERR_BAD_ARG;  // the legacy modes are whole-frame only
         return render_legacy(c, cam, d_rgb, d_linear, st);
     }

@@ -94,7 +94,7 @@ class Scatter(C.Structure):
 
 
 MAT_LAMBERTIAN, MAT_METAL, MAT_DIELECTRIC = 0, 1, 2
-MODE_PATH, MODE_LEGACY_SKY, MODE_LEGACY_FLAT, MODE_LEGACY_NORMAL = 0, 1, 2, 3
+MODE_PATH, MODE_LEGACY_SKY, MODE_LEGACY_FLAT, MODE_LEGACY_NORMAL, MODE_PATH_BVH = 0, 1, 2, 3, 4
 
 
 def d3(v):

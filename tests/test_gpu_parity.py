@@ -361,6 +361,46 @@ def test_device_generate_chapter13_and_bad_args(pkg, gpu, orc):
         gpu.generate(9, 1)                                # unknown kind
 
 
+# ------------------------------------------------------------------ extension: RTZ_MODE_PATH_BVH == brute force
+def _bvh_equals_brute(gpu, cam, shard=None):
+    cam.mode = R.MODE_PATH
+    a, sa = gpu.render(cam, shard)
+    a = a.clone()
+    cam.mode = R.MODE_PATH_BVH
+    b, sb = gpu.render(cam, shard)
+    cam.mode = R.MODE_PATH
+    assert np.array_equal(a.cpu().numpy(), b.cpu().numpy()), int((a != b).sum())
+    assert (sa.samples, sa.segments, sa.depth_capped, sa.absorbed) == (sb.samples, sb.segments, sb.depth_capped, sb.absorbed)
+    return sa, sb
+
+
+def test_bvh_mode_is_bit_identical_to_brute_force(pkg, gpu, orc):
+    """SURVEY 8f row 4, built as a labelled extension: the closest hit through a BVH gives the brute-force image
+    byte for byte (same per-sphere arithmetic, minimum over (t, index)), with far fewer sphere tests."""
+    prng, sp, n = R.final_scene(0xDEADBEEF)
+    gpu.upload(sp, n)
+    sa, sb = _bvh_equals_brute(gpu, R.main_camera(400, 16, seed=0xDEADBEEF))
+    assert sa.sphere_tests == sa.segments * 485 and 0 < sb.sphere_tests < sa.sphere_tests // 10
+    _bvh_equals_brute(gpu, R.main_camera(200, 6, seed=7), pkg.rtz_shard(1, 3, 16, 16))
+    # the hollow glass sphere (nested spheres, rays that start inside a sphere), three cameras
+    sp13, n13 = R.chapter13_scene()
+    gpu.upload(sp13, n13)
+    for preset in CH13_CAMERAS:
+        _bvh_equals_brute(gpu, R.build_camera(400, 16.0 / 9.0, spp=32, seed=0xDEADBEEF, **CH13_CAMERAS[preset]))
+    # one, two and three spheres (root-only hierarchies), an empty world, and the large sweep scenes
+    for k in (0, 1, 2, 3, 5):
+        gpu.upload(sp13, k)
+        _bvh_equals_brute(gpu, R.build_camera(64, 16.0 / 9.0, (-2, 2, 1), (0, 0, -1), 40, spp=4, seed=3))
+    for n_spheres in (512, 4096, 16384):
+        prng = orc.orc_prng_new(0xDEADBEEF)
+        buf = (R.Sphere * n_spheres)()
+        assert orc.orc_generate_sweep(prng, min(n_spheres, 4096), buf) == min(n_spheres, 4096)
+        for i in range(4096, n_spheres):
+            buf[i] = buf[i % 4096]          # duplicated spheres: every hit is a tie that the lower index must win
+        gpu.upload(buf, n_spheres)
+        _bvh_equals_brute(gpu, R.main_camera(96, 3, seed=5))
+
+
 # ------------------------------------------------------------------ edge cases
 def test_edge_cases(pkg, gpu, orc):
     l = pkg.lib()
