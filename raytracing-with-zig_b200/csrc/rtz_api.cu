@@ -194,7 +194,7 @@ int32_t render_path(rtz_context* ctx, const rtz_camera* cam, const rtz::ShardGeo
         // world.hit is made.  Nothing to trace; the zeroed sums resolve to zeros.
     } else if (cam->mode == RTZ_MODE_PATH_BVH) {
         rtz::BvhParams B{P, ctx->bvh_nodes.p, ctx->bvh_order.p, ctx->bvh_wexp.p};
-        rc = launch_trace(ctx, rtz::trace_kernel_bvh<128, 8>, B, P.n_chunks, 128, 0);
+        rc = launch_trace(ctx, rtz::trace_kernel_bvh<128, 6>, B, P.n_chunks, 128, 0);
     } else if (use_const) {
         static thread_local rtz::TraceParamsConst C;  // 8 KiB: keep it off the stack
         C.p = P;

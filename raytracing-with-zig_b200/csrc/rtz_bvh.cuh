@@ -22,7 +22,7 @@ struct BvhNode {
 };
 static_assert(sizeof(BvhNode) == 64, "BvhNode is four float4");
 constexpr int kBvhEmpty = 0x7fffffff;
-constexpr int kBvhMaxDepth = 40;
+constexpr int kBvhMaxDepth = 24;  // median split, leaves of <= 4: 2^20 spheres need 19 levels
 
 struct BvhParams {
     TraceParams p;
@@ -64,9 +64,13 @@ __device__ __forceinline__ bool hit_box(const float* lo, const float* hi, const 
     return tn <= tf;
 }
 
+// Closest hit through the hierarchy.  "While-while" traversal: a warp first walks inner nodes until every lane
+// holds a leaf (or is done), then all lanes test their leaves together, so that box tests and sphere tests
+// are not interleaved lane by lane.  A popped entry whose box lies beyond the current closest hit is skipped.
+constexpr int kBvhDone = (int)0x80000000;
 template <int kBlock>
 __device__ __forceinline__ void bvh_closest_hit(const BvhParams& B, const Path& p, float tmin, float tmax, int* stack,
-                                                float& t_out, int& best_out, unsigned long long& n_tests) {
+                                                float* tstack, float& t_out, int& best_out, unsigned long long& n_tests) {
     const RayK k = ray_constants(p);
     const float tmin_d = tmin * p.len;
     float closest = tmax * p.len;
@@ -75,42 +79,43 @@ __device__ __forceinline__ void bvh_closest_hit(const BvhParams& B, const Path& 
     const float4* geom = B.p.geom;
     int sp = 0;
     int node = 0;
+    auto pop = [&]() {
+        while (sp > 0) {
+            --sp;
+            if (tstack[sp * kBlock] <= closest) return stack[sp * kBlock];
+        }
+        return kBvhDone;
+    };
     for (;;) {
-        const float4* np = reinterpret_cast<const float4*>(B.nodes + node);
-        const float4 n0 = __ldg(np), n1 = __ldg(np + 1), n2 = __ldg(np + 2), n3 = __ldg(np + 3);
-        const float lo0[3] = {n0.x, n0.y, n0.z}, hi0[3] = {n0.w, n1.x, n1.y};
-        const float lo1[3] = {n1.z, n1.w, n2.x}, hi1[3] = {n2.y, n2.z, n2.w};
-        int c0 = __float_as_int(n3.x), c1 = __float_as_int(n3.y);
-        float t0, t1;
-        bool h0 = c0 != kBvhEmpty && hit_box(lo0, hi0, p, ix, iy, iz, tmin_d, closest, t0);
-        bool h1 = c1 != kBvhEmpty && hit_box(lo1, hi1, p, ix, iy, iz, tmin_d, closest, t1);
-        // leaves are tested on the spot
-#pragma unroll
-        for (int side = 0; side < 2; ++side) {
-            const int c = side ? c1 : c0;
-            bool& h = side ? h1 : h0;
-            if (h && c < 0) {
-                const int code = -1 - c, first = code >> 3, cnt = code & 7;
-                for (int q = 0; q < cnt; ++q) {
-                    const int i = __ldg(B.order + first + q);
-                    test_sphere_lex(__ldg(geom + i), __ldg(B.wexp + i), i, p, k, tmin_d, closest, best);
-                }
-                n_tests += (unsigned)cnt;
-                h = false;
+        while (node >= 0) {  // inner nodes
+            const float4* np = reinterpret_cast<const float4*>(B.nodes + node);
+            const float4 n0 = __ldg(np), n1 = __ldg(np + 1), n2 = __ldg(np + 2), n3 = __ldg(np + 3);
+            const float lo0[3] = {n0.x, n0.y, n0.z}, hi0[3] = {n0.w, n1.x, n1.y};
+            const float lo1[3] = {n1.z, n1.w, n2.x}, hi1[3] = {n2.y, n2.z, n2.w};
+            const int c0 = __float_as_int(n3.x), c1 = __float_as_int(n3.y);
+            float t0, t1;
+            const bool h0 = c0 != kBvhEmpty && hit_box(lo0, hi0, p, ix, iy, iz, tmin_d, closest, t0);
+            const bool h1 = c1 != kBvhEmpty && hit_box(lo1, hi1, p, ix, iy, iz, tmin_d, closest, t1);
+            if (h0 && h1) {  // nearer child first, the other on the stack with its entry distance
+                const bool swap = t1 < t0;
+                stack[sp * kBlock] = swap ? c0 : c1;
+                tstack[sp * kBlock] = swap ? t0 : t1;
+                ++sp;
+                node = swap ? c1 : c0;
+            } else if (h0 || h1) {
+                node = h0 ? c0 : c1;
+            } else {
+                node = pop();
             }
         }
-        if (h0 && h1) {  // both inner: nearer first, the other on the stack
-            const bool swap = t1 < t0;
-            stack[sp * kBlock] = swap ? c0 : c1;
-            ++sp;
-            node = swap ? c1 : c0;
-        } else if (h0 || h1) {
-            node = h0 ? c0 : c1;
-        } else {
-            if (sp == 0) break;
-            --sp;
-            node = stack[sp * kBlock];
+        if (node == kBvhDone) break;
+        const int code = -1 - node, first = code >> 3, cnt = code & 7;  // a leaf
+        for (int q = 0; q < cnt; ++q) {
+            const int i = __ldg(B.order + first + q);
+            test_sphere_lex(__ldg(geom + i), __ldg(B.wexp + i), i, p, k, tmin_d, closest, best);
         }
+        n_tests += (unsigned)cnt;
+        node = pop();
     }
     t_out = closest, best_out = best;
 }
@@ -120,8 +125,10 @@ __device__ __forceinline__ void bvh_closest_hit(const BvhParams& B, const Path& 
 template <int kBlock, int kMinBlocks>
 __global__ void __launch_bounds__(kBlock, kMinBlocks) trace_kernel_bvh(const __grid_constant__ BvhParams B) {
     __shared__ int s_stack[kBvhMaxDepth * kBlock];
+    __shared__ float s_tstack[kBvhMaxDepth * kBlock];
     const TraceParams& P = B.p;
     int* stack = s_stack + threadIdx.x;
+    float* tstack = s_tstack + threadIdx.x;
     const unsigned lane = threadIdx.x & 31u;
     const unsigned lt_mask = (1u << lane) - 1u;
     const DevCamera& cam = P.cam;
@@ -167,7 +174,7 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks) trace_kernel_bvh(const __g
         if (S.alive) {
             float t;
             int best;
-            bvh_closest_hit<kBlock>(B, S.path, cam.tmin, cam.tmax, stack, t, best, n_tests);
+            bvh_closest_hit<kBlock>(B, S.path, cam.tmin, cam.tmax, stack, tstack, t, best, n_tests);
             finish_or_continue(P, P.geom, P.aux, P.albedo, S, t, best, n_seg, n_samp, n_cap, n_abs);
         }
         __syncwarp();
