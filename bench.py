@@ -319,6 +319,17 @@ def run_ours(args, rank: int, world: int, local_rank: int):
     }
     if cpu:
         line["cpu_baseline"] = cpu
+    if world == 1:
+        # informational, outside every timed region above: the labelled extension RTZ_MODE_PATH_BVH on the same
+        # frame (same bytes; NOT the reference's brute-force algorithm, so it is neither `value` nor the roofline)
+        try:
+            cam.mode = B.MODE_PATH_BVH
+            ext_ms = min(r.render(cam, shard, out)[1].trace_ms for _ in range(2))
+            line["extension_bvh"] = {"mode": "RTZ_MODE_PATH_BVH", "value": round(W * H * spp / ext_ms / 1e3, 2),
+                                     "unit": "Msamples/s", "trace_ms": round(ext_ms, 3),
+                                     "note": "same image through a BVH over the spheres; not the benchmarked path"}
+        finally:
+            cam.mode = B.MODE_PATH
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
