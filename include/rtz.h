@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define RTZ_ABI_VERSION 1
+#define RTZ_ABI_VERSION 2   /* 2: rtz_stats grew (nan_samples, gpus, gather_ms); rtz_multi_* / rtz_render_multi added */
 
 /* ---- status codes --------------------------------------------------------------- */
 #define RTZ_OK 0
@@ -40,6 +40,7 @@ extern "C" {
 #define RTZ_ERR_TOO_MANY_SPHERES 5 /* more than 2^20 spheres (larger scenes than shared memory   */
                                    /* holds are swept from global memory, they are not an error) */
 #define RTZ_ERR_ARCH 6         /* device is not sm_100 (the library ships sm_100a code only)  */
+#define RTZ_ERR_NCCL 7         /* libnccl.so.2 could not be loaded or an NCCL call failed      */
 
 /* ---- material tags: reference src/material.zig:113-117 (MaterialType) ------------ */
 #define RTZ_MAT_LAMBERTIAN 0
@@ -72,7 +73,10 @@ extern "C" {
  * Dielectric{refractionIndex} :71-74; defaults of MaterialArgs :119-124. */
 typedef struct rtz_sphere {
     double center[3];
-    double radius;            /* already clamped to >= 0 as Sphere.init does (:18-24)         */
+    double radius;            /* > 0 and finite.  Sphere.init clamps negatives to 0 (:18-24); a    */
+                              /* radius-0 sphere makes the reference panic in Vec.divScalar        */
+                              /* (src/vec.zig:39-45) the moment it is hit, so the library refuses  */
+                              /* it (and any non-finite field) with RTZ_ERR_BAD_ARG at upload      */
     int32_t mat_type;         /* RTZ_MAT_*                                                    */
     int32_t reserved;         /* must be 0                                                    */
     double albedo[3];         /* lambertian, metal                                            */
@@ -124,10 +128,18 @@ typedef struct rtz_stats {
     double resolve_ms;         /* resolve / pack kernel                                       */
     double total_ms;           /* first launch -> packed bytes ready on the device            */
     uint64_t seed_used;        /* RNG key actually used (== camera.seed when has_seed)        */
+    uint64_t nan_samples;      /* samples whose colour was NaN (a zero-length scattered direction, */
+                               /* src/vec.zig:126-128 unit of a zero vector); they add 0 to the    */
+                               /* pixel instead of poisoning it, and are COUNTED here, not hidden  */
+    uint32_t gpus;             /* devices that rendered this frame (1 unless rtz_multi_*)          */
+    uint32_t reserved;
+    double gather_ms;          /* multi-GPU: end of the slowest trace kernel -> whole image on     */
+                               /* device 0 (tile exchange over NVLink + de-interleave)             */
 } rtz_stats;
 
 /* ---- whole-frame, host buffers (the drop-in for the body of Camera.render) --------
- * Renders on the current/first CUDA device and writes width*height*3 bytes, row-major,
+ * Renders on the CURRENT CUDA device (one cached context per device; the caller's current device is
+ * left as it was) and writes width*height*3 bytes, row-major,
  * top row first, r,g,b — exactly the bytes PPM.saveBinary emits between header and
  * trailer (src/ppm.zig:51-56).  `stats_out` may be NULL. */
 int32_t rtz_render(const rtz_camera* camera, const rtz_sphere* spheres, uint64_t n_spheres,
@@ -145,8 +157,14 @@ int32_t rtz_write_ppm(const char* path, uint64_t width, uint64_t height, const u
 /* ---- resident API: scene and frame stay in HBM (bench `value`, multi-GPU ranks) ---- */
 typedef struct rtz_context rtz_context;
 
-/* device < 0: use the current device.  stream: a cudaStream_t passed as void*
- * (NULL = the context creates its own non-blocking stream). */
+/* device < 0: use the current device.  stream: a cudaStream_t passed as void*.
+ * NULL = the context creates its OWN non-blocking stream, which is NOT ordered against any other
+ * stream of the caller: device buffers handed to rtz_render_resident / rtz_deinterleave must be
+ * complete before the call (every call blocks until its own work is done, so results are complete
+ * on return).  To order the library's work with the CUDA legacy default stream or the per-thread
+ * default stream pass RTZ_STREAM_LEGACY / RTZ_STREAM_PER_THREAD (CUDA's own handle values). */
+#define RTZ_STREAM_LEGACY ((void*)0x1)
+#define RTZ_STREAM_PER_THREAD ((void*)0x2)
 int32_t rtz_context_create(int32_t device, void* stream, rtz_context** ctx_out);
 int32_t rtz_context_destroy(rtz_context* ctx);
 
@@ -183,6 +201,44 @@ int32_t rtz_render_resident(rtz_context* ctx, const rtz_camera* camera, const rt
 int32_t rtz_deinterleave(rtz_context* ctx, uint64_t width, uint64_t height, uint32_t world,
                          uint32_t tile_w, uint32_t tile_h, const uint8_t* d_gathered,
                          uint8_t* d_rgb_out);
+
+/* ---- N GPUs of ONE box behind the same call (north_star: "rendered on 8xB200" as a drop-in for
+ * Camera.render; SURVEY.md 8b `num_gpus`, 8e "single process ... no host MPI").  ONE host process, no
+ * launcher: the library drives every device itself.  The frame is cut into interleaved tile_w x tile_h
+ * tiles (tile k -> device k % gpus, rtz_shard), every device traces its tiles, and the packed bytes
+ * travel to device 0 over NVLink either
+ *   RTZ_GATHER_P2P   fused into the resolve kernel: each device's resolve writes its pixels straight
+ *                    into device 0's row-major image through peer memory (no staging, no second kernel), or
+ *   RTZ_GATHER_NCCL  ncclCommInitAll + one grouped ncclSend/ncclRecv of the compact tile buffers,
+ *                    then rtz_deinterleave on device 0 (libnccl.so.2 is loaded on first use).
+ * RTZ_GATHER_AUTO picks P2P when every device can map device 0's memory, NCCL otherwise (env RTZ_GATHER=
+ * p2p|nccl overrides).  The image is the single-GPU image BYTE FOR BYTE for any device count and tile
+ * size (integer accumulation, counter-based RNG). */
+#define RTZ_GATHER_AUTO 0
+#define RTZ_GATHER_P2P 1
+#define RTZ_GATHER_NCCL 2
+typedef struct rtz_multi rtz_multi;
+
+/* num_gpus <= 0: every visible device.  devices: num_gpus ordinals, or NULL for 0..num_gpus-1;
+ * devices[0] is "rank 0", where the image lands.  tile_w/tile_h = 0: the default 4x4. */
+int32_t rtz_multi_create(int32_t num_gpus, const int32_t* devices, uint32_t tile_w, uint32_t tile_h,
+                         int32_t gather, rtz_multi** multi_out);
+int32_t rtz_multi_destroy(rtz_multi* multi);
+int32_t rtz_multi_gpus(const rtz_multi* multi);              /* devices in use, or -1            */
+int32_t rtz_multi_gather(const rtz_multi* multi);            /* RTZ_GATHER_P2P or RTZ_GATHER_NCCL */
+/* HittableList for every device (rtz_scene_upload on each). */
+int32_t rtz_multi_scene_upload(rtz_multi* multi, const rtz_sphere* spheres, uint64_t n_spheres);
+/* Camera.render on all devices: launches are enqueued on every device before the first wait.  The
+ * row-major image stays resident on device 0 (*d_rgb_out, optional, receives that DEVICE pointer, valid
+ * until the next call on `multi`); rgb_out (optional, HOST, 3*width*height bytes) receives a copy.
+ * stats_out: work counters summed over the devices, trace_ms = slowest device, total_ms = first launch
+ * -> image complete on device 0 (events on device 0's stream). */
+int32_t rtz_multi_render(rtz_multi* multi, const rtz_camera* camera, uint8_t* rgb_out, uint8_t** d_rgb_out,
+                         rtz_stats* stats_out);
+/* One-shot form with HOST buffers — rtz_render on num_gpus devices (<= 0: all).  Keeps one lazily
+ * created rtz_multi per device count, like rtz_render keeps one context. */
+int32_t rtz_render_multi(const rtz_camera* camera, const rtz_sphere* spheres, uint64_t n_spheres,
+                         int32_t num_gpus, uint8_t* rgb_out, rtz_stats* stats_out);
 
 /* ---- device-side unit probes (one ray; used by the KATs that mirror the reference's
  * own unit tests, src/sphere.zig:76-136, src/hittable.zig:185-209,

@@ -40,7 +40,8 @@ class rtz_stats(C.Structure):
     _fields_ = [("samples", C.c_uint64), ("segments", C.c_uint64), ("sphere_tests", C.c_uint64),
                 ("depth_capped", C.c_uint64), ("absorbed", C.c_uint64), ("kernel_launches", C.c_uint64),
                 ("trace_ms", C.c_double), ("resolve_ms", C.c_double), ("total_ms", C.c_double),
-                ("seed_used", C.c_uint64)]
+                ("seed_used", C.c_uint64), ("nan_samples", C.c_uint64), ("gpus", C.c_uint32), ("reserved", C.c_uint32),
+                ("gather_ms", C.c_double)]
 
 
 class rtz_hit(C.Structure):
@@ -57,7 +58,9 @@ RTZ_OK = 0
 SCENE_FINAL, SCENE_CHAPTER13, SCENE_SWEEP = 0, 1, 2
 MODE_PATH, MODE_PATH_BVH = 0, 4   # MODE_PATH_BVH: extension, same image through a BVH (include/rtz.h)
 ERR_NAMES = {1: "RTZ_ERR_BAD_ARG", 2: "RTZ_ERR_NO_DEVICE", 3: "RTZ_ERR_CUDA", 4: "RTZ_ERR_IO",
-             5: "RTZ_ERR_TOO_MANY_SPHERES", 6: "RTZ_ERR_ARCH"}
+             5: "RTZ_ERR_TOO_MANY_SPHERES", 6: "RTZ_ERR_ARCH", 7: "RTZ_ERR_NCCL"}
+GATHER_AUTO, GATHER_P2P, GATHER_NCCL = 0, 1, 2
+ABI_VERSION = 2
 
 # every symbol include/rtz.h declares, with its signature
 _u8p, _f64p, _f32p = C.POINTER(C.c_uint8), C.POINTER(C.c_double), C.POINTER(C.c_float)
@@ -73,6 +76,13 @@ SIGNATURES = {
     "rtz_shard_pixels": (_u64, [_u64, _u64, C.POINTER(rtz_shard)]),
     "rtz_render_resident": (_i32, [_vp, C.POINTER(rtz_camera), C.POINTER(rtz_shard), _vp, C.POINTER(rtz_stats)]),
     "rtz_deinterleave": (_i32, [_vp, _u64, _u64, _u32, _u32, _u32, _vp, _vp]),
+    "rtz_multi_create": (_i32, [_i32, C.POINTER(_i32), _u32, _u32, _i32, C.POINTER(_vp)]),
+    "rtz_multi_destroy": (_i32, [_vp]),
+    "rtz_multi_gpus": (_i32, [_vp]),
+    "rtz_multi_gather": (_i32, [_vp]),
+    "rtz_multi_scene_upload": (_i32, [_vp, C.POINTER(rtz_sphere), _u64]),
+    "rtz_multi_render": (_i32, [_vp, C.POINTER(rtz_camera), _u8p, C.POINTER(_vp), C.POINTER(rtz_stats)]),
+    "rtz_render_multi": (_i32, [C.POINTER(rtz_camera), C.POINTER(rtz_sphere), _u64, _i32, _u8p, C.POINTER(rtz_stats)]),
     "rtz_probe_hit": (_i32, [C.POINTER(rtz_sphere), _u64, D3, D3, _f64, _f64, C.POINTER(rtz_hit)]),
     "rtz_probe_scatter": (_i32, [C.POINTER(rtz_sphere), _u64, _i32, D3, D3, _u64, _u32, _u32, _u32,
                                  C.POINTER(rtz_scatter)]),

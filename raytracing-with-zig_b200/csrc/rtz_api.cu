@@ -3,6 +3,8 @@
 // (src/ppm.zig:42-60).  There is no CPU fallback anywhere in this file: every compute entry
 // point needs a CUDA device and fails with RTZ_ERR_NO_DEVICE / RTZ_ERR_CUDA otherwise.
 #include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <nccl.h>  // types and prototypes only: libnccl.so.2 is dlopen()ed on first use (rtz_multi_*, RTZ_GATHER_NCCL)
 
 #include <algorithm>
 #include <cerrno>
@@ -10,6 +12,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <map>
 #include <mutex>
 #include <string>
 #include <vector>
@@ -49,6 +52,19 @@ inline float bits_to_float(int32_t v) {
     return f;
 }
 
+// Entry points select the context's device; the caller's current device is restored on return.
+struct DeviceGuard {
+    int saved = -1;
+    DeviceGuard() {
+        if (cudaGetDevice(&saved) != cudaSuccess) saved = -1;
+    }
+    ~DeviceGuard() {
+        if (saved >= 0) cudaSetDevice(saved);
+    }
+};
+
+inline bool finite3(const double v[3]) { return std::isfinite(v[0]) && std::isfinite(v[1]) && std::isfinite(v[2]); }
+
 template <class T>
 struct DevBuf {
     T* p = nullptr;
@@ -82,14 +98,18 @@ struct rtz_context {
     DevBuf<float4> geom, pairs, aux, albedo;
     DevBuf<rtz::DSphere> dspheres;
     std::vector<float4> h_pairs;
-    // RTZ_MODE_PATH_BVH (extension): hierarchy over the same FP32 spheres
+    // RTZ_MODE_PATH_BVH (extension): hierarchy over the same FP32 spheres, built on the first render that
+    // asks for it (h_geom / h_w are the host copies it is built from)
     DevBuf<rtz::BvhNode> bvh_nodes;
     DevBuf<int> bvh_order;
     DevBuf<float> bvh_wexp;
+    std::vector<float4> h_geom;
+    std::vector<float> h_w;
+    bool bvh_ready = false;
     int n_spheres = 0, n_pad = 0;
     // frame state
     DevBuf<unsigned long long> accum;
-    DevBuf<unsigned long long> counters;  // [0] queue head, [1..4] stats
+    DevBuf<unsigned long long> counters;  // [0] queue head, [1..4] stats, [5] BVH tests, [6] NaN samples
     DevBuf<uint8_t> rgb;                  // used by the host-buffer entry points
     DevBuf<double> linear;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
@@ -108,13 +128,22 @@ int32_t shard_geom(uint64_t W, uint64_t H, const rtz_shard* s, rtz::ShardGeom& g
     const uint64_t tiles = (uint64_t)g.tiles_x * g.tiles_y;
     // every rank gets the size of rank 0 (the largest) so gathered buffers are equal-sized
     g.n_local_tiles = (uint32_t)((tiles + d.world - 1) / d.world);
-    g.tile_pixels = d.tile_w * d.tile_h;
+    const uint64_t tile_pixels = (uint64_t)d.tile_w * d.tile_h;
+    if (tile_pixels > 0xFFFFFFFFull || (uint64_t)g.n_local_tiles * tile_pixels > 0xFFFFFFFFull) return RTZ_ERR_BAD_ARG;
+    g.tile_pixels = (uint32_t)tile_pixels;
     return RTZ_OK;
 }
 
 int32_t check_camera(const rtz_camera* c) {
     if (!c || c->width == 0 || c->height == 0) return RTZ_ERR_BAD_ARG;
-    if (c->width * c->height > 0xFFFFFFFFull) return RTZ_ERR_BAD_ARG;
+    if (c->width > 0xFFFFFFFFull || c->height > 0xFFFFFFFFull || c->width * c->height > 0xFFFFFFFFull) return RTZ_ERR_BAD_ARG;
+    // a NaN / infinite camera would only produce NaN samples: refuse it up front (t_max may be +inf, Scene.zig:21)
+    if (!finite3(c->center) || !finite3(c->pixel0) || !finite3(c->du) || !finite3(c->dv) || !finite3(c->defocus_disk_u) ||
+        !finite3(c->defocus_disk_v) || !std::isfinite(c->defocus_angle) || !std::isfinite(c->pixel_samples_scale) ||
+        !std::isfinite(c->t_min) || std::isnan(c->t_max)) {
+        g_last_error = "camera has a non-finite field";
+        return RTZ_ERR_BAD_ARG;
+    }
     if (c->mode < RTZ_MODE_PATH || c->mode > RTZ_MODE_PATH_BVH) return RTZ_ERR_BAD_ARG;
     if (c->samples_per_pixel == 0 || c->samples_per_pixel > 0x7FFFFFFFull) return RTZ_ERR_BAD_ARG;
     if (c->mode != RTZ_MODE_PATH && c->mode != RTZ_MODE_PATH_BVH && c->samples_per_pixel != 1) return RTZ_ERR_BAD_ARG;
@@ -139,11 +168,14 @@ rtz::DevCamera to_dev_camera(const rtz_camera& c, uint64_t seed) {
     return d;
 }
 
-// chunk size: <= 256 samples of one pixel, and enough chunks to keep every warp busy
-uint32_t pick_chunk(uint32_t spp) {
+// Work chunks: <= 256 samples of ONE pixel (RTZ_CHUNK overrides the cap: experiments).
+void pick_chunks(const rtz_context* ctx, rtz::TraceParams& P, uint64_t n_local_pixels) {
+    (void)ctx;
     uint32_t cap = 256u;
-    if (const char* e = std::getenv("RTZ_CHUNK")) cap = (uint32_t)std::max(1, std::atoi(e));  // experiments
-    return spp < cap ? spp : cap;
+    if (const char* e = std::getenv("RTZ_CHUNK")) cap = (uint32_t)std::max(1, std::atoi(e));
+    P.chunk = P.cam.spp < cap ? P.cam.spp : cap;
+    P.chunks_per_pixel = (P.cam.spp + P.chunk - 1) / P.chunk;
+    P.n_chunks = n_local_pixels * P.chunks_per_pixel;
 }
 
 template <class Kern, class Params>
@@ -164,20 +196,35 @@ int32_t launch_trace(rtz_context* ctx, Kern kern, const Params& P, uint64_t n_ch
     return RTZ_OK;
 }
 
-int32_t render_path(rtz_context* ctx, const rtz_camera* cam, const rtz::ShardGeom& sg, uint8_t* d_rgb,
-                    double* d_linear, rtz_stats* st, uint64_t seed) {
+// RTZ_MODE_PATH_BVH (extension) needs the hierarchy: built on the host from the FP32 spheres the first time a
+// render asks for it, so that plain uploads (and every brute-force frame) never pay for it.
+int32_t ensure_bvh(rtz_context* c);
+
+// What one device contributes to a frame.  `image` set: the resolve stores every channel at its place in the
+// ROW-MAJOR image (possibly peer memory of device 0) instead of the compact tile buffer `d_rgb`.
+struct FrameTarget {
+    uint8_t* d_rgb = nullptr;
+    double* d_linear = nullptr;
+    uint8_t* image = nullptr;
+};
+
+// Enqueue the frame (memsets, trace kernel, resolve, counter read-back) on the context's stream; no host wait.
+int32_t enqueue_path(rtz_context* ctx, const rtz_camera* cam, const rtz::ShardGeom& sg, const FrameTarget& out,
+                     uint64_t seed) {
     if (ctx->n_spheres < 0) return RTZ_ERR_BAD_ARG;  // an empty world is a valid HittableList: every ray sees the sky
     const uint64_t n_local_pixels = (uint64_t)sg.n_local_tiles * sg.tile_pixels;
     if (n_local_pixels > 0xFFFFFFFFull) return RTZ_ERR_BAD_ARG;
+    if (cam->mode == RTZ_MODE_PATH_BVH) {
+        const int32_t rc = ensure_bvh(ctx);
+        if (rc != RTZ_OK) return rc;
+    }
     RTZ_CUDA(ctx->accum.reserve(3 * n_local_pixels));
     rtz::TraceParams P;
     P.cam = to_dev_camera(*cam, seed);
     P.sh = sg;
     P.geom = ctx->geom.p, P.pairs = ctx->pairs.p, P.aux = ctx->aux.p, P.albedo = ctx->albedo.p;
     P.n_spheres = ctx->n_spheres, P.n_pad = ctx->n_pad;
-    P.chunk = pick_chunk(P.cam.spp);
-    P.chunks_per_pixel = (P.cam.spp + P.chunk - 1) / P.chunk;
-    P.n_chunks = n_local_pixels * P.chunks_per_pixel;
+    pick_chunks(ctx, P, n_local_pixels);
     P.accum = ctx->accum.p;
     P.counter = ctx->counters.p;
     P.stats = ctx->counters.p + 1;
@@ -206,6 +253,8 @@ int32_t render_path(rtz_context* ctx, const rtz_camera* cam, const rtz::ShardGeo
             rc = launch_trace(ctx, rtz::trace_kernel_const<256, 3>, C, P.n_chunks, 256, 0);
         else if (ctx->variant == 2)
             rc = launch_trace(ctx, rtz::trace_kernel_const<128, 5>, C, P.n_chunks, 128, 0);
+        else if (ctx->variant == 5)  // candidates resolved behind every block (the round-1 schedule): A/B
+            rc = launch_trace(ctx, rtz::trace_kernel_const_nodefer<128, 6>, C, P.n_chunks, 128, 0);
         else
             rc = launch_trace(ctx, rtz::trace_kernel_const<128, 6>, C, P.n_chunks, 128, 0);
     } else if (use_global) {
@@ -235,17 +284,26 @@ int32_t render_path(rtz_context* ctx, const rtz_camera* cam, const rtz::ShardGeo
     if (rc != RTZ_OK) return rc;
     RTZ_CUDA(cudaEventRecord(ctx->ev[2], ctx->stream));
     const uint64_t n3 = 3 * n_local_pixels;
-    rtz::resolve_kernel<<<(unsigned)((n3 + 255) / 256), 256, 0, ctx->stream>>>(
-        ctx->accum.p, n_local_pixels, cam->pixel_samples_scale, d_rgb, d_linear);
+    if (out.image)
+        rtz::resolve_scatter_kernel<<<(unsigned)((n3 + 255) / 256), 256, 0, ctx->stream>>>(
+            ctx->accum.p, sg, (uint32_t)cam->width, (uint32_t)cam->height, cam->pixel_samples_scale, out.image);
+    else
+        rtz::resolve_kernel<<<(unsigned)((n3 + 255) / 256), 256, 0, ctx->stream>>>(
+            ctx->accum.p, n_local_pixels, cam->pixel_samples_scale, out.d_rgb, out.d_linear);
     RTZ_CUDA(cudaGetLastError());
     RTZ_CUDA(cudaEventRecord(ctx->ev[3], ctx->stream));
     RTZ_CUDA(cudaMemcpyAsync(ctx->h_counters, ctx->counters.p, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost,
                              ctx->stream));
+    return RTZ_OK;
+}
+
+// Wait for the frame enqueued by enqueue_path and report the work it did.
+int32_t collect_path(rtz_context* ctx, const rtz_camera* cam, const rtz::ShardGeom& sg, rtz_stats* st, uint64_t seed) {
     RTZ_CUDA(cudaStreamSynchronize(ctx->stream));
     if (st) {
         std::memset(st, 0, sizeof(*st));
         st->samples = ctx->h_counters[1], st->segments = ctx->h_counters[2];
-        if (P.cam.bounce_max == 0) {  // counted on the host: the kernel did not run
+        if (cam->bounce_max == 0) {  // counted on the host: the kernel did not run
             uint64_t px = 0;
             for (uint32_t t = sg.rank; t < (uint64_t)sg.tiles_x * sg.tiles_y; t += sg.world) {
                 const uint32_t ty = t / sg.tiles_x, tx = t - ty * sg.tiles_x;
@@ -257,7 +315,9 @@ int32_t render_path(rtz_context* ctx, const rtz_camera* cam, const rtz::ShardGeo
         }
         st->depth_capped = ctx->h_counters[3], st->absorbed = ctx->h_counters[4];
         st->sphere_tests = cam->mode == RTZ_MODE_PATH_BVH ? ctx->h_counters[5] : st->segments * (uint64_t)ctx->n_spheres;
-        st->kernel_launches = P.cam.bounce_max == 0 ? 1 : 2;
+        st->nan_samples = ctx->h_counters[6];
+        st->kernel_launches = cam->bounce_max == 0 ? 1 : 2;
+        st->gpus = 1;
         float ms = 0;
         cudaEventElapsedTime(&ms, ctx->ev[1], ctx->ev[2]), st->trace_ms = ms;
         cudaEventElapsedTime(&ms, ctx->ev[2], ctx->ev[3]), st->resolve_ms = ms;
@@ -265,6 +325,15 @@ int32_t render_path(rtz_context* ctx, const rtz_camera* cam, const rtz::ShardGeo
         st->seed_used = seed;
     }
     return RTZ_OK;
+}
+
+int32_t render_path(rtz_context* ctx, const rtz_camera* cam, const rtz::ShardGeom& sg, uint8_t* d_rgb,
+                    double* d_linear, rtz_stats* st, uint64_t seed) {
+    FrameTarget out;
+    out.d_rgb = d_rgb, out.d_linear = d_linear;
+    const int32_t rc = enqueue_path(ctx, cam, sg, out, seed);
+    if (rc != RTZ_OK) return rc;
+    return collect_path(ctx, cam, sg, st, seed);
 }
 
 int32_t render_legacy(rtz_context* ctx, const rtz_camera* cam, uint8_t* d_rgb, double* d_linear, rtz_stats* st) {
@@ -314,6 +383,7 @@ const char* rtz_strerror(int32_t s) {
         case RTZ_ERR_IO: return "I/O error";
         case RTZ_ERR_TOO_MANY_SPHERES: return "scene does not fit in shared memory";
         case RTZ_ERR_ARCH: return "device is not sm_100 (librtz ships sm_100a code only)";
+        case RTZ_ERR_NCCL: return "NCCL error (libnccl.so.2 missing or a collective failed)";
         default: return "unknown status";
     }
 }
@@ -338,12 +408,13 @@ int32_t rtz_context_create(int32_t device, void* stream, rtz_context** out) {
     int n = 0;
     int32_t rc = rtz_device_count(&n);
     if (rc != RTZ_OK) return rc;
+    DeviceGuard guard;
     if (device < 0) RTZ_CUDA(cudaGetDevice(&device));
     if (device >= n) return RTZ_ERR_BAD_ARG;
     RTZ_CUDA(cudaSetDevice(device));
     cudaDeviceProp prop;
     RTZ_CUDA(cudaGetDeviceProperties(&prop, device));
-    if (prop.major != 10) {
+    if (prop.major != 10 || prop.minor != 0) {  // sm_100a SASS only runs on compute capability 10.0
         g_last_error = std::string("device ") + prop.name + " is sm_" + std::to_string(prop.major * 10 + prop.minor);
         return RTZ_ERR_ARCH;
     }
@@ -377,6 +448,7 @@ int32_t rtz_context_create(int32_t device, void* stream, rtz_context** out) {
 
 int32_t rtz_context_destroy(rtz_context* c) {
     if (!c) return RTZ_ERR_BAD_ARG;
+    DeviceGuard guard;
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
     c->geom.release(), c->pairs.release(), c->aux.release(), c->albedo.release(), c->dspheres.release();
@@ -453,6 +525,7 @@ struct BvhBuilder {
 
 int32_t rtz_scene_upload(rtz_context* c, const rtz_sphere* sp, uint64_t n) {
     if (!c || (!sp && n) || n > (1u << 20)) return RTZ_ERR_BAD_ARG;
+    DeviceGuard guard;
     RTZ_CUDA(cudaSetDevice(c->device));
     const int n_pad = (int)((n + 7) & ~7ull);
     std::vector<float4> g(n_pad ? n_pad : 1), pr(n_pad ? n_pad : 1), a(n_pad ? n_pad : 1), al(n_pad ? n_pad : 1);
@@ -462,6 +535,15 @@ int32_t rtz_scene_upload(rtz_context* c, const rtz_sphere* sp, uint64_t n) {
         const rtz_sphere& s = sp[i];
         if (s.mat_type < RTZ_MAT_LAMBERTIAN || s.mat_type > RTZ_MAT_DIELECTRIC) return RTZ_ERR_BAD_ARG;
         const float r = (float)(s.radius < 0 ? 0.0 : s.radius);  // Sphere.init clamp (src/sphere.zig:21)
+        // A radius-0 sphere makes the reference panic in Vec.divScalar (src/vec.zig:39-45) when it is hit, and
+        // NaN / infinite geometry only yields NaN samples: both are refused here instead of rendered wrongly.
+        const bool mat_ok = s.mat_type == RTZ_MAT_DIELECTRIC
+                                ? (std::isfinite(s.refraction_index) && (float)s.refraction_index != 0.0f)
+                                : (finite3(s.albedo) && (s.mat_type != RTZ_MAT_METAL || std::isfinite(s.fuzz)));
+        if (!finite3(s.center) || !std::isfinite(s.radius) || !(r > 0.0f) || !mat_ok) {
+            g_last_error = "sphere " + std::to_string(i) + ": radius must be > 0 and every field of its material finite";
+            return RTZ_ERR_BAD_ARG;
+        }
         const float cx = (float)s.center[0], cy = (float)s.center[1], cz = (float)s.center[2];
         // q = |c|^2 - r^2 of the FP32-rounded sphere, evaluated in f64 and rounded once
         const double q = ((double)cx * cx + (double)cy * cy + (double)cz * cz) - (double)r * r;
@@ -484,11 +566,17 @@ int32_t rtz_scene_upload(rtz_context* c, const rtz_sphere* sp, uint64_t n) {
         pr[2 * p] = make_float4(A.x, B.x, A.y, B.y);
         pr[2 * p + 1] = make_float4(A.z, B.z, w[2 * p], w[2 * p + 1]);
     }
+    // Not failure-atomic by itself (growing a buffer frees the old one), so the context holds NO scene from here
+    // until every copy has been enqueued: a failed upload leaves an empty world behind, never stale geometry.
+    c->n_spheres = c->n_pad = 0;
+    c->h_pairs.clear(), c->h_geom.clear(), c->h_w.clear();
+    c->bvh_ready = false;
     if (n_pad) {
         RTZ_CUDA(c->geom.reserve(n_pad));
         RTZ_CUDA(c->pairs.reserve(n_pad));
         RTZ_CUDA(c->aux.reserve(n_pad));
         RTZ_CUDA(c->albedo.reserve(n_pad));
+        // pageable sources: cudaMemcpyAsync returns once the bytes are staged, so the vectors may die at return
         RTZ_CUDA(cudaMemcpyAsync(c->geom.p, g.data(), n_pad * sizeof(float4), cudaMemcpyHostToDevice, c->stream));
         RTZ_CUDA(cudaMemcpyAsync(c->pairs.p, pr.data(), n_pad * sizeof(float4), cudaMemcpyHostToDevice, c->stream));
         RTZ_CUDA(cudaMemcpyAsync(c->aux.p, a.data(), n_pad * sizeof(float4), cudaMemcpyHostToDevice, c->stream));
@@ -497,26 +585,42 @@ int32_t rtz_scene_upload(rtz_context* c, const rtz_sphere* sp, uint64_t n) {
     RTZ_CUDA(c->dspheres.reserve(ds.size()));
     RTZ_CUDA(cudaMemcpyAsync(c->dspheres.p, ds.data(), ds.size() * sizeof(rtz::DSphere), cudaMemcpyHostToDevice,
                              c->stream));
-    BvhBuilder bvh(g, (int)n);
-    bvh.run();
-    RTZ_CUDA(c->bvh_nodes.reserve(bvh.nodes.size()));
-    RTZ_CUDA(c->bvh_order.reserve(std::max<size_t>(1, bvh.order.size())));
-    RTZ_CUDA(c->bvh_wexp.reserve(std::max<size_t>(1, (size_t)n)));
-    RTZ_CUDA(cudaMemcpyAsync(c->bvh_nodes.p, bvh.nodes.data(), bvh.nodes.size() * sizeof(rtz::BvhNode), cudaMemcpyHostToDevice, c->stream));
-    if (n) {
-        RTZ_CUDA(cudaMemcpyAsync(c->bvh_order.p, bvh.order.data(), n * sizeof(int), cudaMemcpyHostToDevice, c->stream));
-        RTZ_CUDA(cudaMemcpyAsync(c->bvh_wexp.p, w.data(), n * sizeof(float), cudaMemcpyHostToDevice, c->stream));
-    }
-    RTZ_CUDA(cudaStreamSynchronize(c->stream));  // the staging vectors die here
-    c->h_pairs = pr;  // host copy: small scenes can travel to the kernel as a __grid_constant__ parameter
+    c->h_pairs.swap(pr);  // host copy: small scenes travel to the kernel as a __grid_constant__ parameter
+    g.resize(n), w.resize(n);
+    c->h_geom.swap(g), c->h_w.swap(w);  // what the BVH extension is built from, if it is ever asked for
     c->n_spheres = (int)n, c->n_pad = n_pad;
     return RTZ_OK;
 }
+
+}  // extern "C"
+
+namespace {
+int32_t ensure_bvh(rtz_context* c) {
+    if (c->bvh_ready) return RTZ_OK;
+    const size_t n = (size_t)c->n_spheres;
+    BvhBuilder bvh(c->h_geom, (int)n);
+    bvh.run();
+    RTZ_CUDA(c->bvh_nodes.reserve(bvh.nodes.size()));
+    RTZ_CUDA(c->bvh_order.reserve(std::max<size_t>(1, bvh.order.size())));
+    RTZ_CUDA(c->bvh_wexp.reserve(std::max<size_t>(1, n)));
+    RTZ_CUDA(cudaMemcpyAsync(c->bvh_nodes.p, bvh.nodes.data(), bvh.nodes.size() * sizeof(rtz::BvhNode), cudaMemcpyHostToDevice, c->stream));
+    if (n) {
+        RTZ_CUDA(cudaMemcpyAsync(c->bvh_order.p, bvh.order.data(), n * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+        RTZ_CUDA(cudaMemcpyAsync(c->bvh_wexp.p, c->h_w.data(), n * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+    }
+    RTZ_CUDA(cudaStreamSynchronize(c->stream));
+    c->bvh_ready = true;
+    return RTZ_OK;
+}
+}  // namespace
+
+extern "C" {
 
 int32_t rtz_scene_generate(rtz_context* c, int32_t kind, uint64_t seed, uint64_t n_spheres, rtz_sphere* out,
                            uint64_t cap, uint64_t* n_out, uint64_t state_out[4]) {
     if (!c || kind < RTZ_SCENE_FINAL || kind > RTZ_SCENE_SWEEP) return RTZ_ERR_BAD_ARG;
     if (kind == RTZ_SCENE_SWEEP && (n_spheres < 4 || n_spheres > (1u << 20))) return RTZ_ERR_BAD_ARG;
+    DeviceGuard guard;
     RTZ_CUDA(cudaSetDevice(c->device));
     // capacity of the device list: the final scene has at most 22*22 + 4 spheres, the sweep exactly n
     const uint64_t dev_cap = kind == RTZ_SCENE_SWEEP ? n_spheres : 22 * 22 + 4;
@@ -562,6 +666,7 @@ static int32_t render_resident_impl(rtz_context* c, const rtz_camera* cam, const
     if (!c || !d_rgb) return RTZ_ERR_BAD_ARG;
     int32_t rc = check_camera(cam);
     if (rc != RTZ_OK) return rc;
+    DeviceGuard guard;
     RTZ_CUDA(cudaSetDevice(c->device));
     if (cam->mode != RTZ_MODE_PATH && cam->mode != RTZ_MODE_PATH_BVH) {
         if (shard && shard->world != 1) return RTZ_ERR_BAD_ARG;  // the legacy modes are whole-frame only
@@ -586,6 +691,8 @@ int32_t rtz_deinterleave(rtz_context* c, uint64_t W, uint64_t H, uint32_t world,
     rtz::ShardGeom g;
     int32_t rc = shard_geom(W, H, &s, g);
     if (rc != RTZ_OK) return rc;
+    if (W > 0xFFFFFFFFull || H > 0xFFFFFFFFull || W * H > 0xFFFFFFFFull) return RTZ_ERR_BAD_ARG;
+    DeviceGuard guard;
     RTZ_CUDA(cudaSetDevice(c->device));
     const uint64_t n = W * H;
     rtz::deinterleave_kernel<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(
@@ -595,29 +702,38 @@ int32_t rtz_deinterleave(rtz_context* c, uint64_t W, uint64_t H, uint32_t world,
     return RTZ_OK;
 }
 
-// The host-buffer entry points keep ONE lazily created context per process (buffers and stream are
-// reused from frame to frame; nothing of the caller's is retained).
+// The host-buffer entry points keep ONE lazily created context per DEVICE (buffers and stream are reused
+// from frame to frame; nothing of the caller's is retained).  A call renders on the caller's current device.
 static std::mutex g_default_mu;
-static rtz_context* g_default_ctx = nullptr;
+static std::map<int, rtz_context*> g_default_ctx;
 
 int32_t rtz_render_linear(const rtz_camera* cam, const rtz_sphere* sp, uint64_t n, uint8_t* rgb_out,
                           double* linear_out, rtz_stats* st) {
     if (!rgb_out || (!sp && n)) return RTZ_ERR_BAD_ARG;
     int32_t rc = check_camera(cam);
     if (rc != RTZ_OK) return rc;
+    int cnt = 0;
+    rc = rtz_device_count(&cnt);
+    if (rc != RTZ_OK) return rc;
     std::lock_guard<std::mutex> lock(g_default_mu);
-    if (!g_default_ctx) {
-        rc = rtz_context_create(-1, nullptr, &g_default_ctx);
+    DeviceGuard guard;
+    int dev = 0;
+    RTZ_CUDA(cudaGetDevice(&dev));
+    rtz_context*& slot = g_default_ctx[dev];
+    if (!slot) {
+        rc = rtz_context_create(dev, nullptr, &slot);
         if (rc != RTZ_OK) return rc;
     }
-    rtz_context* c = g_default_ctx;
+    rtz_context* c = slot;
     rc = rtz_scene_upload(c, sp, n);
     if (rc != RTZ_OK) return rc;
+    RTZ_CUDA(cudaSetDevice(c->device));
     const uint64_t px = cam->width * cam->height;
     RTZ_CUDA(c->rgb.reserve(3 * px));
     if (linear_out) RTZ_CUDA(c->linear.reserve(3 * px));
     rc = render_resident_impl(c, cam, nullptr, c->rgb.p, linear_out ? c->linear.p : nullptr, st);
     if (rc != RTZ_OK) return rc;
+    RTZ_CUDA(cudaSetDevice(c->device));
     RTZ_CUDA(cudaMemcpyAsync(rgb_out, c->rgb.p, 3 * px, cudaMemcpyDeviceToHost, c->stream));
     if (linear_out)
         RTZ_CUDA(cudaMemcpyAsync(linear_out, c->linear.p, 3 * px * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
@@ -630,7 +746,7 @@ int32_t rtz_render(const rtz_camera* cam, const rtz_sphere* sp, uint64_t n, uint
 }
 
 int32_t rtz_write_ppm(const char* path, uint64_t w, uint64_t h, const uint8_t* rgb) {
-    if (!path || (!rgb && w * h)) return RTZ_ERR_BAD_ARG;
+    if (!path || w > 0xFFFFFFFFull || h > 0xFFFFFFFFull || (!rgb && w * h)) return RTZ_ERR_BAD_ARG;
     FILE* f = std::fopen(path, "wb");
     if (!f) {
         g_last_error = std::string(path) + ": " + std::strerror(errno);
@@ -643,6 +759,319 @@ int32_t rtz_write_ppm(const char* path, uint64_t w, uint64_t h, const uint8_t* r
     ok = (std::fclose(f) == 0) && ok;
     return ok ? RTZ_OK : RTZ_ERR_IO;
 }
+
+}  // extern "C" (first part)
+
+// ---- N GPUs of one box behind the same call ----------------------------------------------------------
+namespace {
+
+// NCCL entry points, resolved from libnccl.so.2 at run time so that single-GPU users need no NCCL at all.
+struct NcclApi {
+    void* handle = nullptr;
+    decltype(&ncclCommInitAll) CommInitAll = nullptr;
+    decltype(&ncclCommDestroy) CommDestroy = nullptr;
+    decltype(&ncclSend) Send = nullptr;
+    decltype(&ncclRecv) Recv = nullptr;
+    decltype(&ncclGroupStart) GroupStart = nullptr;
+    decltype(&ncclGroupEnd) GroupEnd = nullptr;
+    decltype(&ncclGetErrorString) GetErrorString = nullptr;
+    bool load() {
+        if (handle) return true;
+        for (const char* name : {"libnccl.so.2", "libnccl.so"}) {
+            handle = dlopen(name, RTLD_NOW | RTLD_GLOBAL);
+            if (handle) break;
+        }
+        if (!handle) {
+            g_last_error = std::string("dlopen(libnccl.so.2): ") + dlerror();
+            return false;
+        }
+#define RTZ_NCCL_SYM(field, sym)                                              \
+    field = reinterpret_cast<decltype(field)>(dlsym(handle, #sym));            \
+    if (!field) {                                                              \
+        g_last_error = "libnccl.so.2 lacks " #sym;                             \
+        return false;                                                          \
+    }
+        RTZ_NCCL_SYM(CommInitAll, ncclCommInitAll)
+        RTZ_NCCL_SYM(CommDestroy, ncclCommDestroy)
+        RTZ_NCCL_SYM(Send, ncclSend)
+        RTZ_NCCL_SYM(Recv, ncclRecv)
+        RTZ_NCCL_SYM(GroupStart, ncclGroupStart)
+        RTZ_NCCL_SYM(GroupEnd, ncclGroupEnd)
+        RTZ_NCCL_SYM(GetErrorString, ncclGetErrorString)
+#undef RTZ_NCCL_SYM
+        return true;
+    }
+};
+NcclApi g_nccl;
+
+#define RTZ_NCCL(call)                                                                  \
+    do {                                                                                \
+        ncclResult_t r_ = (call);                                                       \
+        if (r_ != ncclSuccess) {                                                        \
+            g_last_error = std::string(#call) + ": " + g_nccl.GetErrorString(r_);       \
+            return RTZ_ERR_NCCL;                                                        \
+        }                                                                               \
+    } while (0)
+
+}  // namespace
+
+struct rtz_multi {
+    std::vector<int> dev;
+    std::vector<rtz_context*> ctx;
+    std::vector<cudaEvent_t> done;        // per device: its resolve has finished
+    uint32_t tile_w = 4, tile_h = 4;
+    int gather = RTZ_GATHER_P2P;
+    std::vector<ncclComm_t> comms;        // RTZ_GATHER_NCCL
+    std::vector<uint8_t*> local;          // RTZ_GATHER_NCCL: per-device compact tile buffer (device r), r >= 1
+    std::vector<size_t> local_cap;
+    DevBuf<uint8_t> gathered;             // RTZ_GATHER_NCCL, device 0: `world` compact buffers back to back
+    DevBuf<uint8_t> image;                // device 0: the row-major frame
+    cudaEvent_t ev_start = nullptr, ev_traced = nullptr, ev_end = nullptr;  // device 0's stream
+};
+
+extern "C" {
+
+int32_t rtz_multi_destroy(rtz_multi* m) {
+    if (!m) return RTZ_ERR_BAD_ARG;
+    DeviceGuard guard;
+    for (size_t r = 0; r < m->ctx.size(); ++r) {
+        if (!m->ctx[r]) continue;
+        cudaSetDevice(m->dev[r]);
+        cudaStreamSynchronize(m->ctx[r]->stream);
+        if (r < m->local.size() && m->local[r]) cudaFree(m->local[r]);
+        if (r < m->done.size() && m->done[r]) cudaEventDestroy(m->done[r]);
+    }
+    for (ncclComm_t c : m->comms)
+        if (c && g_nccl.CommDestroy) g_nccl.CommDestroy(c);
+    if (!m->dev.empty()) {
+        cudaSetDevice(m->dev[0]);
+        m->gathered.release(), m->image.release();
+        for (cudaEvent_t e : {m->ev_start, m->ev_traced, m->ev_end})
+            if (e) cudaEventDestroy(e);
+    }
+    for (rtz_context* c : m->ctx)
+        if (c) rtz_context_destroy(c);
+    delete m;
+    return RTZ_OK;
+}
+
+int32_t rtz_multi_create(int32_t num_gpus, const int32_t* devices, uint32_t tile_w, uint32_t tile_h, int32_t gather,
+                         rtz_multi** out) {
+    if (!out || gather < RTZ_GATHER_AUTO || gather > RTZ_GATHER_NCCL) return RTZ_ERR_BAD_ARG;
+    *out = nullptr;
+    int visible = 0;
+    int32_t rc = rtz_device_count(&visible);
+    if (rc != RTZ_OK) return rc;
+    if (num_gpus <= 0) num_gpus = visible;
+    if (num_gpus > visible) {
+        g_last_error = "asked for " + std::to_string(num_gpus) + " GPUs, " + std::to_string(visible) + " visible";
+        return RTZ_ERR_BAD_ARG;
+    }
+    DeviceGuard guard;
+    rtz_multi* m = new rtz_multi();
+    m->tile_w = tile_w ? tile_w : 4, m->tile_h = tile_h ? tile_h : 4;
+    m->dev.resize(num_gpus), m->ctx.assign(num_gpus, nullptr), m->done.assign(num_gpus, nullptr);
+    m->local.assign(num_gpus, nullptr), m->local_cap.assign(num_gpus, 0);
+    for (int r = 0; r < num_gpus; ++r) {
+        m->dev[r] = devices ? devices[r] : r;
+        for (int q = 0; q < r; ++q)
+            if (m->dev[q] == m->dev[r]) rc = RTZ_ERR_BAD_ARG;  // a device may appear once
+        if (rc == RTZ_OK) rc = rtz_context_create(m->dev[r], nullptr, &m->ctx[r]);
+        if (rc != RTZ_OK) {
+            rtz_multi_destroy(m);
+            return rc;
+        }
+        cudaSetDevice(m->dev[r]);
+        cudaEventCreateWithFlags(&m->done[r], cudaEventDisableTiming);
+    }
+    cudaSetDevice(m->dev[0]);
+    cudaEventCreate(&m->ev_start), cudaEventCreate(&m->ev_traced), cudaEventCreate(&m->ev_end);
+    if (const char* e = std::getenv("RTZ_GATHER")) {
+        if (!std::strcmp(e, "p2p")) gather = RTZ_GATHER_P2P;
+        if (!std::strcmp(e, "nccl")) gather = RTZ_GATHER_NCCL;
+    }
+    // peer mapping of device 0's memory into every other device (the fused resolve + gather writes through it)
+    bool p2p_ok = true;
+    if (gather != RTZ_GATHER_NCCL) {
+        for (int r = 1; r < num_gpus && p2p_ok; ++r) {
+            int can = 0;
+            cudaDeviceCanAccessPeer(&can, m->dev[r], m->dev[0]);
+            if (!can) {
+                p2p_ok = false;
+                break;
+            }
+            cudaSetDevice(m->dev[r]);
+            const cudaError_t e = cudaDeviceEnablePeerAccess(m->dev[0], 0);
+            if (e == cudaErrorPeerAccessAlreadyEnabled) cudaGetLastError();
+            else if (e != cudaSuccess) p2p_ok = false, cudaGetLastError();
+        }
+        if (!p2p_ok && gather == RTZ_GATHER_P2P) {
+            g_last_error = "RTZ_GATHER_P2P: device 0's memory cannot be mapped into every other device";
+            rtz_multi_destroy(m);
+            return RTZ_ERR_CUDA;
+        }
+    }
+    m->gather = (gather == RTZ_GATHER_NCCL || !p2p_ok) ? RTZ_GATHER_NCCL : RTZ_GATHER_P2P;
+    if (m->gather == RTZ_GATHER_NCCL && num_gpus > 1) {
+        if (!g_nccl.load()) {
+            rtz_multi_destroy(m);
+            return RTZ_ERR_NCCL;
+        }
+        m->comms.assign(num_gpus, nullptr);
+        const ncclResult_t r = g_nccl.CommInitAll(m->comms.data(), num_gpus, m->dev.data());
+        if (r != ncclSuccess) {
+            g_last_error = std::string("ncclCommInitAll: ") + g_nccl.GetErrorString(r);
+            m->comms.clear();
+            rtz_multi_destroy(m);
+            return RTZ_ERR_NCCL;
+        }
+    }
+    *out = m;
+    return RTZ_OK;
+}
+
+int32_t rtz_multi_gpus(const rtz_multi* m) { return m ? (int32_t)m->ctx.size() : -1; }
+int32_t rtz_multi_gather(const rtz_multi* m) { return m ? m->gather : -1; }
+
+int32_t rtz_multi_scene_upload(rtz_multi* m, const rtz_sphere* sp, uint64_t n) {
+    if (!m) return RTZ_ERR_BAD_ARG;
+    for (rtz_context* c : m->ctx) {
+        const int32_t rc = rtz_scene_upload(c, sp, n);
+        if (rc != RTZ_OK) return rc;
+    }
+    return RTZ_OK;
+}
+
+int32_t rtz_multi_render(rtz_multi* m, const rtz_camera* cam, uint8_t* rgb_out, uint8_t** d_rgb_out, rtz_stats* st) {
+    if (!m) return RTZ_ERR_BAD_ARG;
+    int32_t rc = check_camera(cam);
+    if (rc != RTZ_OK) return rc;
+    DeviceGuard guard;
+    const int world = (int)m->ctx.size();
+    rtz_context* c0 = m->ctx[0];
+    const uint64_t px = cam->width * cam->height;
+    RTZ_CUDA(cudaSetDevice(m->dev[0]));
+    RTZ_CUDA(m->image.reserve(3 * px));
+    if (d_rgb_out) *d_rgb_out = m->image.p;
+    const bool path_mode = cam->mode == RTZ_MODE_PATH || cam->mode == RTZ_MODE_PATH_BVH;
+    if (!path_mode || world == 1) {
+        // the deterministic legacy modes are 90 000 rays: one device; and one device needs no exchange
+        rc = render_resident_impl(c0, cam, nullptr, m->image.p, nullptr, st);
+        if (rc != RTZ_OK) return rc;
+        RTZ_CUDA(cudaSetDevice(m->dev[0]));
+        if (rgb_out) {
+            RTZ_CUDA(cudaMemcpyAsync(rgb_out, m->image.p, 3 * px, cudaMemcpyDeviceToHost, c0->stream));
+            RTZ_CUDA(cudaStreamSynchronize(c0->stream));
+        }
+        return RTZ_OK;
+    }
+    const uint64_t seed = cam->has_seed ? cam->seed : os_seed();  // ONE key for the whole frame
+    std::vector<rtz::ShardGeom> sg(world);
+    for (int r = 0; r < world; ++r) {
+        const rtz_shard sh{(uint32_t)r, (uint32_t)world, m->tile_w, m->tile_h};
+        rc = shard_geom(cam->width, cam->height, &sh, sg[r]);
+        if (rc != RTZ_OK) return rc;
+    }
+    const size_t per_rank = 3 * (size_t)sg[0].n_local_tiles * sg[0].tile_pixels;  // equal on every rank
+    const bool nccl = m->gather == RTZ_GATHER_NCCL;
+    if (nccl) {
+        RTZ_CUDA(m->gathered.reserve(per_rank * world));
+        for (int r = 1; r < world; ++r) {
+            if (m->local_cap[r] >= per_rank) continue;
+            RTZ_CUDA(cudaSetDevice(m->dev[r]));
+            if (m->local[r]) cudaFree(m->local[r]);
+            m->local[r] = nullptr, m->local_cap[r] = 0;
+            RTZ_CUDA(cudaMalloc(&m->local[r], per_rank));
+            m->local_cap[r] = per_rank;
+        }
+        RTZ_CUDA(cudaSetDevice(m->dev[0]));
+    }
+    RTZ_CUDA(cudaEventRecord(m->ev_start, c0->stream));
+    // every device's frame is enqueued before the first wait
+    for (int r = 0; r < world; ++r) {
+        RTZ_CUDA(cudaSetDevice(m->dev[r]));
+        FrameTarget out;
+        if (nccl)
+            out.d_rgb = r == 0 ? m->gathered.p : m->local[r];
+        else
+            out.image = m->image.p;  // peer memory for r >= 1
+        rc = enqueue_path(m->ctx[r], cam, sg[r], out, seed);
+        if (rc != RTZ_OK) return rc;
+        RTZ_CUDA(cudaEventRecord(m->done[r], m->ctx[r]->stream));
+    }
+    RTZ_CUDA(cudaSetDevice(m->dev[0]));
+    RTZ_CUDA(cudaEventRecord(m->ev_traced, c0->stream));
+    if (nccl) {
+        RTZ_NCCL(g_nccl.GroupStart());
+        for (int r = 1; r < world; ++r) {
+            RTZ_NCCL(g_nccl.Send(m->local[r], per_rank, ncclUint8, 0, m->comms[r], m->ctx[r]->stream));
+            RTZ_NCCL(g_nccl.Recv(m->gathered.p + per_rank * r, per_rank, ncclUint8, r, m->comms[0], c0->stream));
+        }
+        RTZ_NCCL(g_nccl.GroupEnd());
+        RTZ_CUDA(cudaSetDevice(m->dev[0]));
+        rtz::deinterleave_kernel<<<(unsigned)((px + 255) / 256), 256, 0, c0->stream>>>(
+            m->gathered.p, (uint64_t)sg[0].n_local_tiles * sg[0].tile_pixels, (uint32_t)cam->width, (uint32_t)cam->height,
+            (uint32_t)world, m->tile_w, m->tile_h, sg[0].tiles_x, m->image.p);
+        RTZ_CUDA(cudaGetLastError());
+    } else {
+        for (int r = 1; r < world; ++r) RTZ_CUDA(cudaStreamWaitEvent(c0->stream, m->done[r], 0));
+    }
+    RTZ_CUDA(cudaEventRecord(m->ev_end, c0->stream));
+    if (rgb_out) RTZ_CUDA(cudaMemcpyAsync(rgb_out, m->image.p, 3 * px, cudaMemcpyDeviceToHost, c0->stream));
+    rtz_stats total;
+    std::memset(&total, 0, sizeof total);
+    for (int r = 0; r < world; ++r) {
+        RTZ_CUDA(cudaSetDevice(m->dev[r]));
+        rtz_stats one;
+        rc = collect_path(m->ctx[r], cam, sg[r], &one, seed);
+        if (rc != RTZ_OK) return rc;
+        total.samples += one.samples, total.segments += one.segments, total.sphere_tests += one.sphere_tests;
+        total.depth_capped += one.depth_capped, total.absorbed += one.absorbed, total.nan_samples += one.nan_samples;
+        total.kernel_launches += one.kernel_launches;
+        total.trace_ms = std::max(total.trace_ms, one.trace_ms);
+        total.resolve_ms = std::max(total.resolve_ms, one.resolve_ms);
+    }
+    RTZ_CUDA(cudaSetDevice(m->dev[0]));
+    RTZ_CUDA(cudaStreamSynchronize(c0->stream));
+    if (st) {
+        float ms = 0;
+        cudaEventElapsedTime(&ms, m->ev_start, m->ev_end), total.total_ms = ms;
+        total.gather_ms = std::max(0.0, total.total_ms - total.trace_ms);
+        total.kernel_launches += nccl ? 1 : 0;
+        total.gpus = (uint32_t)world;
+        total.seed_used = seed;
+        *st = total;
+    }
+    return RTZ_OK;
+}
+
+// one lazily created rtz_multi per device count for the one-shot form
+static std::mutex g_multi_mu;
+static std::map<int, rtz_multi*> g_multi;
+
+int32_t rtz_render_multi(const rtz_camera* cam, const rtz_sphere* sp, uint64_t n, int32_t num_gpus, uint8_t* rgb_out,
+                         rtz_stats* st) {
+    if (!rgb_out || (!sp && n)) return RTZ_ERR_BAD_ARG;
+    int32_t rc = check_camera(cam);
+    if (rc != RTZ_OK) return rc;
+    int visible = 0;
+    rc = rtz_device_count(&visible);
+    if (rc != RTZ_OK) return rc;
+    if (num_gpus <= 0) num_gpus = visible;
+    std::lock_guard<std::mutex> lock(g_multi_mu);
+    rtz_multi*& slot = g_multi[num_gpus];
+    if (!slot) {
+        rc = rtz_multi_create(num_gpus, nullptr, 0, 0, RTZ_GATHER_AUTO, &slot);
+        if (rc != RTZ_OK) return rc;
+    }
+    rc = rtz_multi_scene_upload(slot, sp, n);
+    if (rc != RTZ_OK) return rc;
+    return rtz_multi_render(slot, cam, rgb_out, nullptr, st);
+}
+
+}  // extern "C"
+
+extern "C" {
 
 // ---- probes -------------------------------------------------------------------------------------
 int32_t rtz_probe_hit(const rtz_sphere* sp, uint64_t n, const double o[3], const double d[3], double tmin, double tmax,
@@ -711,8 +1140,9 @@ int32_t rtz_probe_to_rgb(const double* lin, uint64_t n, uint8_t* rgb_out) {
     ScopedCtx sc;
     int32_t rc = rtz_context_create(-1, nullptr, &sc.c);
     if (rc != RTZ_OK) return rc;
-    double* dl;
-    uint8_t* dr;
+    double* dl = nullptr;
+    uint8_t* dr = nullptr;
+    if (n > (1ull << 32)) return RTZ_ERR_BAD_ARG;
     RTZ_CUDA(cudaMalloc(&dl, 3 * n * sizeof(double)));
     cudaError_t e = cudaMalloc(&dr, 3 * n);
     if (e == cudaSuccess) e = cudaMemcpyAsync(dl, lin, 3 * n * sizeof(double), cudaMemcpyHostToDevice, sc.c->stream);

@@ -31,12 +31,13 @@ struct TraceParams {
     uint64_t n_chunks;      // n_local_pixels(padded) * chunks_per_pixel
     unsigned long long* accum;    // [n_local_pixels*3] 32.32 fixed-point colour sums
     unsigned long long* counter;  // work-queue head
-    unsigned long long* stats;    // {samples, segments, depth_capped, absorbed}
+    unsigned long long* stats;    // {samples, segments, depth_capped, absorbed, (BVH tests), NaN samples}
 };
 
 // Scenes of up to kMaxConstSpheres spheres travel as a __grid_constant__ kernel parameter: the
 // sweep then reads them through the constant bank with uniform loads (LDCU -> uniform registers
 // -> UR operands of FADD2/FFMA2), which needs no LDS, no vector registers and no shared memory.
+constexpr int kConstDefer = 8;          // constant-bank kernel: candidates are resolved every 8 blocks (256 spheres)
 constexpr int kMaxConstSpheres = 512;  // 8 KiB: what the constant cache serves at full rate (1024 spheres already thrash it: measured)
 struct TraceParamsConst {
     TraceParams p;
@@ -153,16 +154,29 @@ __device__ __forceinline__ void test_pair(const float4 p0, const float4 p1, cons
 // n_pad is a multiple of 8; padding spheres have w = -inf -> disc = -inf -> never a candidate.
 // kConstBank selects two register-allocation nudges that were measured per kernel (same arithmetic):
 // the constant-bank kernel pins 2*o (+0.8 %), the shared-memory kernel forms t_min*len late (+4 % at N = 1024).
-template <bool kConstBank>
+//
+// kDefer > 0: DEFERRED candidate resolution.  Resolving a block's candidates right behind its 32 tests makes
+// the warp enter a divergent region 16 times per sweep at N = 485 (some lane nearly always has a candidate,
+// ~9 of 32 lanes active: 9 % of the kernel's warp-instructions).  Instead every lane appends the block's
+// (mask, base) to a private list in shared memory — one unconditional store, the count advances only for a
+// non-empty mask, no branch — and the lists are resolved every kDefer blocks: the divergent region is entered
+// n_blocks / kDefer times, and inside it every lane walks ITS OWN candidates, so the warp pays the maximum
+// over the lanes of their candidate counts, not their sum over the blocks.  The candidates of a path are
+// still evaluated in ascending sphere order with the same shrinking t_max: same arithmetic, same image.
+// `defer` = [2 slots][kDefer entries][kBlock threads] uint2, bank = thread: conflict-free.
+template <bool kConstBank, int kDefer, int kBlock>
 __device__ __forceinline__ void sweep2(const float4* __restrict__ pairs, const float4* __restrict__ gather, int n_pad,
                                        float tmin, float tmax, const Path& a, const Path& b, float& ta, int& ia,
-                                       float& tb, int& ib) {
+                                       float& tb, int& ib, uint2* __restrict__ defer) {
     RayK ka = ray_constants(a), kb = ray_constants(b);
     // pin 2*o in registers: left alone, ptxas keeps o and re-adds it for every block of 32 spheres
     if (kConstBank) asm volatile("" : "+f"(ka.tx), "+f"(ka.ty), "+f"(ka.tz), "+f"(kb.tx), "+f"(kb.ty), "+f"(kb.tz));
     // Interval(t_min, t_max) of Scene.interval in distance units (directions are unit length)
     float ca = tmax * a.len, cb = tmax * b.len;
     int ba = -1, bb = -1;
+    uint2* const list_a = defer + threadIdx.x;                     // entry e: list_a[e * kBlock]
+    uint2* const list_b = defer + kDefer * kBlock + threadIdx.x;
+    int na = 0, nb = 0, pending = 0;
     for (int base = 0; base < n_pad; base += 32) {
         const int cnt = min(32, n_pad - base);
         unsigned ma = 0xFFFFFFFFu, mb = 0xFFFFFFFFu;  // 1 = miss
@@ -177,7 +191,25 @@ __device__ __forceinline__ void sweep2(const float4* __restrict__ pairs, const f
             }
         }
         const unsigned canda = ~ma, candb = ~mb;
-        if (canda | candb) {
+        if (kDefer > 0) {
+            list_a[na * kBlock] = make_uint2(canda, (unsigned)base);
+            list_b[nb * kBlock] = make_uint2(candb, (unsigned)base);
+            na += canda != 0u, nb += candb != 0u;
+            if (++pending < kDefer && base + 32 < n_pad) continue;  // warp-uniform
+            pending = 0;
+            float la = a.len, lb = b.len;
+            if (!kConstBank) asm volatile("" : "+f"(la), "+f"(lb));
+            for (int e = 0; e < na; ++e) {
+                const uint2 v = list_a[e * kBlock];
+                resolve_candidates(gather, v.x, (int)v.y, min(32, n_pad - (int)v.y), a, tmin * la, ca, ba);
+            }
+            for (int e = 0; e < nb; ++e) {
+                const uint2 v = list_b[e * kBlock];
+                resolve_candidates(gather, v.x, (int)v.y, min(32, n_pad - (int)v.y), b, tmin * lb, cb, bb);
+            }
+            na = nb = 0;
+            __syncwarp();  // reconverge before the next block's uniform sweep
+        } else if (canda | candb) {
             // t_min * len is formed HERE, behind an opaque copy, so that it does not occupy two more
             // registers across the whole sweep of the shared-memory kernel (96 registers at 5 CTAs per SM)
             float la = a.len, lb = b.len;
@@ -202,6 +234,7 @@ __device__ __forceinline__ void finish_or_continue(const TraceParams& P, const f
         if (fr) atomicAdd(px + 0, fr);
         if (fg) atomicAdd(px + 1, fg);
         if (fb) atomicAdd(px + 2, fb);
+        if (sr != sr || sg != sg || sb != sb) atomicAdd(P.stats + 5, 1ULL);  // NaN sample: adds 0, but is counted
         ++n_samp;
         n_cap += (term == 2), n_abs += (term == 1);
         s.alive = false;
@@ -210,9 +243,9 @@ __device__ __forceinline__ void finish_or_continue(const TraceParams& P, const f
 
 // The body shared by the two kernels below.  `geo` is the warp-uniform geometry the sweep reads,
 // `gather` the copy for per-lane lookups (candidate roots, hit records).
-template <bool kConstBank>
+template <bool kConstBank, int kDefer, int kBlock>
 __device__ __forceinline__ void trace_body(const TraceParams& P, const float4* __restrict__ pairs,
-                                           const float4* __restrict__ gather) {
+                                           const float4* __restrict__ gather, uint2* __restrict__ defer) {
     // material rows are touched once per HIT (not per test): they stay in global memory / L1
     const float4* s_aux = P.aux;
     const float4* s_alb = P.albedo;
@@ -283,7 +316,7 @@ __device__ __forceinline__ void trace_body(const TraceParams& P, const float4* _
         if (__ballot_sync(0xFFFFFFFFu, A.alive || B.alive) == 0u) break;  // queue drained, every path finished
         float ta, tb;
         int ia, ib;
-        sweep2<kConstBank>(pairs, gather, P.n_pad, cam.tmin, cam.tmax, A.path, B.path, ta, ia, tb, ib);
+        sweep2<kConstBank, kDefer, kBlock>(pairs, gather, P.n_pad, cam.tmin, cam.tmax, A.path, B.path, ta, ia, tb, ib, defer);
         if (A.alive) finish_or_continue(P, gather, s_aux, s_alb, A, ta, ia, n_seg, n_samp, n_cap, n_abs);
         if (B.alive) finish_or_continue(P, gather, s_aux, s_alb, B, tb, ib, n_seg, n_samp, n_cap, n_abs);
         // explicit reconvergence point: with it ptxas proves the loop top converged (no BRA.DIV before
@@ -524,6 +557,7 @@ __device__ __forceinline__ void trace_body_parked(const TraceParams& P, const fl
                     if (fr) atomicAdd(px + 0, fr);
                     if (fg) atomicAdd(px + 1, fg);
                     if (fb) atomicAdd(px + 2, fb);
+                    if (sr != sr || sg != sg || sb != sb) atomicAdd(P.stats + 5, 1ULL);
                     ++n_samp;
                     n_cap += (term == 2), n_abs += (term == 1);
                     alive &= ~(1u << s);
@@ -562,7 +596,13 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks) trace_kernel_const_parked(
 // no register-file bandwidth, which is what bounds FFMA2 on sm_100.  No shared memory at all.
 template <int kBlock, int kMinBlocks>
 __global__ void __launch_bounds__(kBlock, kMinBlocks) trace_kernel_const(const __grid_constant__ TraceParamsConst C) {
-    trace_body<true>(C.p, C.pairs, C.p.geom);
+    __shared__ uint2 defer[2 * kConstDefer * kBlock];  // 16 KiB at 128 threads
+    trace_body<true, kConstDefer, kBlock>(C.p, C.pairs, C.p.geom, defer);
+}
+// the same kernel resolving every block's candidates at once (RTZ_VARIANT=5: A/B of the deferred lists)
+template <int kBlock, int kMinBlocks>
+__global__ void __launch_bounds__(kBlock, kMinBlocks) trace_kernel_const_nodefer(const __grid_constant__ TraceParamsConst C) {
+    trace_body<true, 0, kBlock>(C.p, C.pairs, C.p.geom, nullptr);
 }
 
 // K1b: geometry staged into shared memory by 1-D TMA bulk copies (cp.async.bulk + mbarrier): scenes
@@ -585,7 +625,7 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks) trace_kernel_smem(const __
         bulk_g2s(s_geom, P.geom, bytes, &s_bar);
     }
     mbar_wait(&s_bar, 0);
-    trace_body<false>(P, s_pairs, s_geom);
+    trace_body<false, 0, kBlock>(P, s_pairs, s_geom, nullptr);
 }
 
 // K1c: geometry read from global memory (L1 / L2, warp-uniform addresses): scenes whose 32 B per sphere do
@@ -593,7 +633,7 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks) trace_kernel_smem(const __
 // limit (src/hittable.zig:43-62), so neither has the drop-in; the sweep just loses its staging.
 template <int kBlock, int kMinBlocks>
 __global__ void __launch_bounds__(kBlock, kMinBlocks) trace_kernel_global(const __grid_constant__ TraceParams P) {
-    trace_body<false>(P, P.pairs, P.geom);
+    trace_body<false, 0, kBlock>(P, P.pairs, P.geom, nullptr);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -614,6 +654,19 @@ __global__ void resolve_kernel(const unsigned long long* __restrict__ accum, uin
     const double lin = ((double)accum[i] * 0x1p-32) * scale;
     rgb[i] = to_byte(lin);
     if (linear) linear[i] = lin;
+}
+
+// K3 fused with the multi-GPU tile exchange (rtz_multi_*, RTZ_GATHER_P2P): the same resolve, but every channel
+// is stored at its place in the ROW-MAJOR image, which lives on device 0 — peer memory over NVLink for the
+// other devices.  A device's resolve IS its half of the gather: no staging buffer, no de-interleave pass.
+__global__ void resolve_scatter_kernel(const unsigned long long* __restrict__ accum, const ShardGeom sh, uint32_t W,
+                                       uint32_t H, double scale, uint8_t* __restrict__ image) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;  // one thread per channel
+    if (i >= 3ull * sh.n_local_tiles * sh.tile_pixels) return;
+    const uint32_t lp = (uint32_t)(i / 3), ch = (uint32_t)(i - 3ull * lp);
+    uint32_t x, y;
+    if (!local_to_global(sh, W, H, lp, x, y)) return;  // tile padding
+    image[3ull * ((uint64_t)y * W + x) + ch] = to_byte(((double)accum[i] * 0x1p-32) * scale);
 }
 
 // ---------------------------------------------------------------------------------------------

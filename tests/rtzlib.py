@@ -68,6 +68,10 @@ class Stats(C.Structure):
         ("resolve_ms", C.c_double),
         ("total_ms", C.c_double),
         ("seed_used", C.c_uint64),
+        ("nan_samples", C.c_uint64),
+        ("gpus", C.c_uint32),
+        ("reserved", C.c_uint32),
+        ("gather_ms", C.c_double),
     ]
 
 

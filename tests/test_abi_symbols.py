@@ -23,7 +23,7 @@ def test_exports_every_declared_symbol(pkg):
     assert not missing, missing
     # the ctypes binding covers the same set
     assert sorted(pkg.binding.SIGNATURES) == names
-    assert pkg.lib().rtz_abi_version() == 1
+    assert pkg.lib().rtz_abi_version() == 2
 
 
 def test_struct_layouts_match_header(pkg):
