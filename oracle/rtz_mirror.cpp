@@ -6,8 +6,8 @@
 // src/material.zig:27-110, src/color.zig:63-80), but evaluated the way the B200 kernels
 // evaluate them: FP32, explicit fmaf, unit ray directions, candidate test on the discriminant
 // expanded around per-ray constants, roots from the direct form, exact c = 0 for the sphere the ray
-// starts on, Philox4x32-10 keyed (seed; pixel, sample, bounce, block),
-// Marsaglia unit vectors, 32.32 fixed-point pixel sums, f64 resolve.
+// starts on, Philox4x32-10 keyed (seed; pixel, sample, bounce, 0), closed-form unit vectors and lens
+// points (polynomial sine / cosine), 32.32 fixed-point pixel sums, f64 resolve.
 //
 // Because every operation is an IEEE-754 correctly rounded +,-,*,/,sqrt or fma, the GPU must
 // reproduce these numbers BIT FOR BIT; tests/test_gpu_parity.py asserts exactly that on the
@@ -56,28 +56,43 @@ struct Rng {
 };
 
 inline float u01(uint32_t x) { return (float)(x >> 8) * 0x1p-24f; }
-inline float u11(uint32_t x) { return std::fmaf(2.0f, u01(x), -1.0f); }
 
-// disk rejection: attempts are (x,y),(z,w) of block 0, (x,y),(z,w) of block 1, ...;
-// skip_first drops the very first attempt (the camera spends block 0's x,y on the pixel jitter)
-inline void sampleDisk(const Rng& g, uint32_t bounce, const uint32_t first[4], bool skip_first, float& a, float& b,
-                       float& s) {
-    uint32_t r[4] = {first[0], first[1], first[2], first[3]};
-    uint32_t blk = 0;
-    for (int attempt = skip_first ? 1 : 0;; ++attempt) {
-        if (attempt && (attempt & 1) == 0) g.block(bounce, ++blk, r);
-        const int o = (attempt & 1) * 2;
-        a = u11(r[o]), b = u11(r[o + 1]);
-        s = std::fmaf(b, b, a * a);
-        if (s < 1.0f) return;
-    }
+// (cos 2*pi*u, sin 2*pi*u), u = (x >> 8) * 2^-24: quarter turn from the top two bits, degree-4 minimax
+// polynomials in the fraction of the quarter (the device's cos_sin_2pi, operation for operation)
+inline void cosSin2Pi(uint32_t x, float& c, float& s) {
+    const uint32_t q = x >> 30;
+    const float f = (float)((x >> 8) & 0x3FFFFFu) * 0x1p-22f;
+    const float z = f * f;
+    float sp = std::fmaf(z, 0x1.3e7abap-13f, -0x1.3259fap-8f);
+    sp = std::fmaf(z, sp, 0x1.46693cp-4f);
+    sp = std::fmaf(z, sp, -0x1.4abbc6p-1f);
+    sp = std::fmaf(z, sp, 0x1.921fb6p+0f);
+    sp = sp * f;
+    float cp = std::fmaf(z, 0x1.c29b9cp-11f, -0x1.550192p-6f);
+    cp = std::fmaf(z, cp, 0x1.03bd86p-2f);
+    cp = std::fmaf(z, cp, -0x1.3bd3aep+0f);
+    cp = std::fmaf(z, cp, 1.0f);
+    const float a = (q & 1u) ? sp : cp;
+    const float b = (q & 1u) ? cp : sp;
+    c = (q == 1u || q == 2u) ? -a : a;
+    s = (q >= 2u) ? -b : b;
 }
 
-inline F3 randomUnitVec(const Rng& g, uint32_t bounce, const uint32_t block0[4]) {
-    float a, b, s;
-    sampleDisk(g, bounce, block0, false, a, b, s);
-    const float q = 2.0f * std::sqrt(1.0f - s);
-    return {a * q, b * q, std::fmaf(-2.0f, s, 1.0f)};
+// uniform in the unit disk, closed form: radius sqrt(u1), angle 2*pi*u2
+inline void sampleDisk(uint32_t x1, uint32_t x2, float& a, float& b) {
+    const float rad = std::sqrt(u01(x1));
+    float c, s;
+    cosSin2Pi(x2, c, s);
+    a = rad * c, b = rad * s;
+}
+
+// uniform on the unit sphere, closed form: z uniform in (-1, 1], angle 2*pi*u2
+inline F3 randomUnitVec(uint32_t x1, uint32_t x2) {
+    const float z = std::fmaf(-2.0f, u01(x1), 1.0f);
+    const float rad = std::sqrt(std::fmaf(-z, z, 1.0f));
+    float c, s;
+    cosSin2Pi(x2, c, s);
+    return {rad * c, rad * s, z};
 }
 
 struct Path {
@@ -105,8 +120,8 @@ inline void cameraRay(const MCamera& c, const Rng& g, uint32_t i, uint32_t j, Pa
     const float psz = std::fmaf(c.dv.z, sy, std::fmaf(c.du.z, sx, c.p0.z));
     p.o = c.c;
     if (c.defocus) {
-        float a, b, s;
-        sampleDisk(g, 0, r, true, a, b, s);
+        float a, b;
+        sampleDisk(r[2], r[3], a, b);
         p.o = {std::fmaf(c.vv.x, b, std::fmaf(c.uu.x, a, c.c.x)), std::fmaf(c.vv.y, b, std::fmaf(c.uu.y, a, c.c.y)),
                std::fmaf(c.vv.z, b, std::fmaf(c.uu.z, a, c.c.z))};
     }
@@ -194,7 +209,7 @@ inline bool shade(const MCamera& cam, const Rng& g, const std::vector<MSphere>& 
             ndx = std::fmaf(kk, nx, ex), ndy = std::fmaf(kk, ny, ey), ndz = std::fmaf(kk, nz, ez);
         }
     } else {
-        const F3 u = randomUnitVec(g, stream, r0);
+        const F3 u = randomUnitVec(r0[1], r0[2]);
         if (s.type == RTZ_MAT_LAMBERTIAN) {
             ndx = nx + u.x, ndy = ny + u.y, ndz = nz + u.z;
             if (ndx < 1e-8f && ndy < 1e-8f && ndz < 1e-8f) ndx = nx, ndy = ny, ndz = nz;

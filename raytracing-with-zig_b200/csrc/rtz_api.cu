@@ -96,13 +96,13 @@ struct rtz_context {
                              // RTZ_GEO_CONST=0 forces the TMA + shared-memory kernel
     // scene (device SoA f32 + the f64 copy the legacy kernel reads)
     DevBuf<float4> geom, pairs, aux, albedo;
+    DevBuf<float> wexp;  // w of the pair layout as a plain row
     DevBuf<rtz::DSphere> dspheres;
     std::vector<float4> h_pairs;
     // RTZ_MODE_PATH_BVH (extension): hierarchy over the same FP32 spheres, built on the first render that
     // asks for it (h_geom / h_w are the host copies it is built from)
     DevBuf<rtz::BvhNode> bvh_nodes;
     DevBuf<int> bvh_order;
-    DevBuf<float> bvh_wexp;
     std::vector<float4> h_geom;
     std::vector<float> h_w;
     bool bvh_ready = false;
@@ -110,6 +110,10 @@ struct rtz_context {
     // frame state
     DevBuf<unsigned long long> accum;
     DevBuf<unsigned long long> counters;  // [0] queue head, [1..4] stats, [5] BVH tests, [6] NaN samples
+    DevBuf<uint32_t> order;               // queue order of the frame (classify_kernel) + its two cursors
+    uint64_t frame_launches = 0;          // kernels launched for the frame in flight
+    int n_dielectric = 0;                 // spheres of glass in the scene: without any, the queue keeps image order
+    DevBuf<unsigned long long> timeline;  // RTZ_TIMELINE=1: per-warp {start, queue dry, done} stamps of the last frame
     DevBuf<uint8_t> rgb;                  // used by the host-buffer entry points
     DevBuf<double> linear;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
@@ -168,14 +172,32 @@ rtz::DevCamera to_dev_camera(const rtz_camera& c, uint64_t seed) {
     return d;
 }
 
-// Work chunks: <= 256 samples of ONE pixel (RTZ_CHUNK overrides the cap: experiments).
-void pick_chunks(const rtz_context* ctx, rtz::TraceParams& P, uint64_t n_local_pixels) {
-    (void)ctx;
-    uint32_t cap = 256u;
+// Work chunks (TraceParams): runs of <= 256 samples of ONE pixel, except for the last pixels of the queue, which
+// are cut ACROSS pixels (32 pixels x one sample index).  The tail region holds about four big chunks per resident
+// warp: enough small work for the early finishers while the others end their last big chunk, even an expensive
+// one.  `tail` = false: no tail region (kernels whose regeneration only knows one-pixel chunks).
+// RTZ_CHUNK / RTZ_TAIL_WIDTH (0 = no tail region) / RTZ_TAIL_CHUNKS / RTZ_COOP_MAX override (experiments; the
+// image does not depend on any of them: tested).
+void pick_chunks(const rtz_context* ctx, rtz::TraceParams& P, uint64_t n_local_pixels, bool tail) {
+    uint32_t cap = 256u, width = 32u, per_warp = 4u, coop = 16u;
     if (const char* e = std::getenv("RTZ_CHUNK")) cap = (uint32_t)std::max(1, std::atoi(e));
-    P.chunk = P.cam.spp < cap ? P.cam.spp : cap;
-    P.chunks_per_pixel = (P.cam.spp + P.chunk - 1) / P.chunk;
-    P.n_chunks = n_local_pixels * P.chunks_per_pixel;
+    if (const char* e = std::getenv("RTZ_TAIL_WIDTH")) width = (uint32_t)std::min(64, std::max(0, std::atoi(e)));
+    if (const char* e = std::getenv("RTZ_TAIL_CHUNKS")) per_warp = (uint32_t)std::max(0, std::atoi(e));
+    if (const char* e = std::getenv("RTZ_COOP_MAX")) coop = (uint32_t)std::max(0, std::atoi(e));
+    const uint32_t spp = P.cam.spp;
+    P.chunk = spp < cap ? spp : cap;
+    P.chunks_per_pixel = (spp + P.chunk - 1) / P.chunk;
+    const uint64_t resident_warps = (uint64_t)ctx->sm_count * 24;
+    uint64_t tail_pixels = (resident_warps * P.chunk * per_warp + spp - 1) / spp;
+    tail_pixels = std::min<uint64_t>(tail_pixels, n_local_pixels);
+    if (!tail || width == 0) tail_pixels = 0;
+    P.tail_width = width ? width : 1;
+    P.tail_blocks = (uint32_t)((tail_pixels + P.tail_width - 1) / P.tail_width);
+    P.tail_first_pixel = (uint32_t)(n_local_pixels - tail_pixels);
+    P.n_local_pixels = (uint32_t)n_local_pixels;
+    P.n_body_chunks = (uint64_t)P.tail_first_pixel * P.chunks_per_pixel;
+    P.n_chunks = P.n_body_chunks + (uint64_t)P.tail_blocks * spp;
+    P.coop_max = coop;
 }
 
 template <class Kern, class Params>
@@ -222,25 +244,49 @@ int32_t enqueue_path(rtz_context* ctx, const rtz_camera* cam, const rtz::ShardGe
     rtz::TraceParams P;
     P.cam = to_dev_camera(*cam, seed);
     P.sh = sg;
-    P.geom = ctx->geom.p, P.pairs = ctx->pairs.p, P.aux = ctx->aux.p, P.albedo = ctx->albedo.p;
+    P.geom = ctx->geom.p, P.pairs = ctx->pairs.p, P.aux = ctx->aux.p, P.albedo = ctx->albedo.p, P.wexp = ctx->wexp.p;
     P.n_spheres = ctx->n_spheres, P.n_pad = ctx->n_pad;
-    pick_chunks(ctx, P, n_local_pixels);
+    pick_chunks(ctx, P, n_local_pixels, cam->mode == RTZ_MODE_PATH && ctx->variant != 4);
     P.accum = ctx->accum.p;
     P.counter = ctx->counters.p;
     P.stats = ctx->counters.p + 1;
+    P.timeline = nullptr;
+    if (const char* e = std::getenv("RTZ_TIMELINE")) {  // diagnostics: tools/tail_timeline.py reads the file back
+        if (e[0] == '1') {
+            RTZ_CUDA(ctx->timeline.reserve(6 * 65536));
+            RTZ_CUDA(cudaMemsetAsync(ctx->timeline.p, 0, 6 * 65536 * sizeof(unsigned long long), ctx->stream));
+            P.timeline = ctx->timeline.p;
+        }
+    }
     const bool use_const = ctx->n_pad <= rtz::kMaxConstSpheres && ctx->geo_const;
     const size_t smem = use_const ? 0 : (size_t)ctx->n_pad * 32;  // pair layout + per-lane rows
-    const bool use_global = !use_const && smem + 1024 > ctx->smem_optin;  // too large to stage: read it from L1/L2
+    // too large to stage next to the kernel's own static shared memory (ray staging rows): read it from L1/L2
+    cudaFuncAttributes fa{};
+    RTZ_CUDA(cudaFuncGetAttributes(&fa, rtz::trace_kernel_smem<512, 1>));
+    const bool use_global = !use_const && smem + fa.sharedSizeBytes + 1024 > ctx->smem_optin;
     RTZ_CUDA(cudaEventRecord(ctx->ev[0], ctx->stream));
     RTZ_CUDA(cudaMemsetAsync(ctx->accum.p, 0, 3 * n_local_pixels * sizeof(unsigned long long), ctx->stream));
     RTZ_CUDA(cudaMemsetAsync(ctx->counters.p, 0, 8 * sizeof(unsigned long long), ctx->stream));
     RTZ_CUDA(cudaEventRecord(ctx->ev[1], ctx->stream));
+    // queue order: pixels that look into glass first (RTZ_ORDER=0: image order)
+    P.order = nullptr;
+    ctx->frame_launches = P.cam.bounce_max == 0 ? 1 : 2;
+    const char* oe = std::getenv("RTZ_ORDER");
+    if (ctx->n_dielectric > 0 && P.cam.bounce_max > 1 && n_local_pixels > 1 && !(oe && oe[0] == '0')) {
+        RTZ_CUDA(ctx->order.reserve(n_local_pixels + 2));
+        unsigned int* cursors = ctx->order.p + n_local_pixels;
+        RTZ_CUDA(cudaMemsetAsync(cursors, 0, 2 * sizeof(unsigned int), ctx->stream));
+        rtz::classify_kernel<<<(unsigned)((n_local_pixels + 127) / 128), 128, 0, ctx->stream>>>(P, ctx->order.p, cursors);
+        RTZ_CUDA(cudaGetLastError());
+        P.order = ctx->order.p;
+        ctx->frame_launches = 3;
+    }
     int32_t rc = RTZ_OK;
     if (P.cam.bounce_max == 0) {
         // `while (bounces < bounceMax)` never runs (src/camera.zig:153): every sample is black and no
         // world.hit is made.  Nothing to trace; the zeroed sums resolve to zeros.
     } else if (cam->mode == RTZ_MODE_PATH_BVH) {
-        rtz::BvhParams B{P, ctx->bvh_nodes.p, ctx->bvh_order.p, ctx->bvh_wexp.p};
+        rtz::BvhParams B{P, ctx->bvh_nodes.p, ctx->bvh_order.p, ctx->wexp.p};
         rc = launch_trace(ctx, rtz::trace_kernel_bvh<128, 6>, B, P.n_chunks, 128, 0);
     } else if (use_const) {
         static thread_local rtz::TraceParamsConst C;  // 8 KiB: keep it off the stack
@@ -253,8 +299,6 @@ int32_t enqueue_path(rtz_context* ctx, const rtz_camera* cam, const rtz::ShardGe
             rc = launch_trace(ctx, rtz::trace_kernel_const<256, 3>, C, P.n_chunks, 256, 0);
         else if (ctx->variant == 2)
             rc = launch_trace(ctx, rtz::trace_kernel_const<128, 5>, C, P.n_chunks, 128, 0);
-        else if (ctx->variant == 5)  // candidates resolved behind every block (the round-1 schedule): A/B
-            rc = launch_trace(ctx, rtz::trace_kernel_const_nodefer<128, 6>, C, P.n_chunks, 128, 0);
         else
             rc = launch_trace(ctx, rtz::trace_kernel_const<128, 6>, C, P.n_chunks, 128, 0);
     } else if (use_global) {
@@ -300,6 +344,16 @@ int32_t enqueue_path(rtz_context* ctx, const rtz_camera* cam, const rtz::ShardGe
 // Wait for the frame enqueued by enqueue_path and report the work it did.
 int32_t collect_path(rtz_context* ctx, const rtz_camera* cam, const rtz::ShardGeom& sg, rtz_stats* st, uint64_t seed) {
     RTZ_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (const char* path = std::getenv("RTZ_TIMELINE_OUT")) {
+        if (ctx->timeline.p && std::getenv("RTZ_TIMELINE") && std::getenv("RTZ_TIMELINE")[0] == '1') {
+            std::vector<unsigned long long> h(6 * 65536);
+            RTZ_CUDA(cudaMemcpy(h.data(), ctx->timeline.p, h.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+            if (FILE* f = std::fopen(path, "wb")) {
+                std::fwrite(h.data(), sizeof(unsigned long long), h.size(), f);
+                std::fclose(f);
+            }
+        }
+    }
     if (st) {
         std::memset(st, 0, sizeof(*st));
         st->samples = ctx->h_counters[1], st->segments = ctx->h_counters[2];
@@ -316,7 +370,7 @@ int32_t collect_path(rtz_context* ctx, const rtz_camera* cam, const rtz::ShardGe
         st->depth_capped = ctx->h_counters[3], st->absorbed = ctx->h_counters[4];
         st->sphere_tests = cam->mode == RTZ_MODE_PATH_BVH ? ctx->h_counters[5] : st->segments * (uint64_t)ctx->n_spheres;
         st->nan_samples = ctx->h_counters[6];
-        st->kernel_launches = cam->bounce_max == 0 ? 1 : 2;
+        st->kernel_launches = ctx->frame_launches;
         st->gpus = 1;
         float ms = 0;
         cudaEventElapsedTime(&ms, ctx->ev[1], ctx->ev[2]), st->trace_ms = ms;
@@ -452,8 +506,8 @@ int32_t rtz_context_destroy(rtz_context* c) {
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
     c->geom.release(), c->pairs.release(), c->aux.release(), c->albedo.release(), c->dspheres.release();
-    c->accum.release(), c->counters.release(), c->rgb.release(), c->linear.release();
-    c->bvh_nodes.release(), c->bvh_order.release(), c->bvh_wexp.release();
+    c->accum.release(), c->counters.release(), c->rgb.release(), c->linear.release(), c->timeline.release(), c->order.release();
+    c->bvh_nodes.release(), c->bvh_order.release(), c->wexp.release();
     for (auto& e : c->ev)
         if (e) cudaEventDestroy(e);
     if (c->h_counters) cudaFreeHost(c->h_counters);
@@ -576,6 +630,8 @@ int32_t rtz_scene_upload(rtz_context* c, const rtz_sphere* sp, uint64_t n) {
         RTZ_CUDA(c->pairs.reserve(n_pad));
         RTZ_CUDA(c->aux.reserve(n_pad));
         RTZ_CUDA(c->albedo.reserve(n_pad));
+        RTZ_CUDA(c->wexp.reserve(n_pad));
+        RTZ_CUDA(cudaMemcpyAsync(c->wexp.p, w.data(), n_pad * sizeof(float), cudaMemcpyHostToDevice, c->stream));
         // pageable sources: cudaMemcpyAsync returns once the bytes are staged, so the vectors may die at return
         RTZ_CUDA(cudaMemcpyAsync(c->geom.p, g.data(), n_pad * sizeof(float4), cudaMemcpyHostToDevice, c->stream));
         RTZ_CUDA(cudaMemcpyAsync(c->pairs.p, pr.data(), n_pad * sizeof(float4), cudaMemcpyHostToDevice, c->stream));
@@ -589,6 +645,8 @@ int32_t rtz_scene_upload(rtz_context* c, const rtz_sphere* sp, uint64_t n) {
     g.resize(n), w.resize(n);
     c->h_geom.swap(g), c->h_w.swap(w);  // what the BVH extension is built from, if it is ever asked for
     c->n_spheres = (int)n, c->n_pad = n_pad;
+    c->n_dielectric = 0;
+    for (uint64_t i = 0; i < n; ++i) c->n_dielectric += sp[i].mat_type == RTZ_MAT_DIELECTRIC;
     return RTZ_OK;
 }
 
@@ -602,11 +660,9 @@ int32_t ensure_bvh(rtz_context* c) {
     bvh.run();
     RTZ_CUDA(c->bvh_nodes.reserve(bvh.nodes.size()));
     RTZ_CUDA(c->bvh_order.reserve(std::max<size_t>(1, bvh.order.size())));
-    RTZ_CUDA(c->bvh_wexp.reserve(std::max<size_t>(1, n)));
     RTZ_CUDA(cudaMemcpyAsync(c->bvh_nodes.p, bvh.nodes.data(), bvh.nodes.size() * sizeof(rtz::BvhNode), cudaMemcpyHostToDevice, c->stream));
     if (n) {
         RTZ_CUDA(cudaMemcpyAsync(c->bvh_order.p, bvh.order.data(), n * sizeof(int), cudaMemcpyHostToDevice, c->stream));
-        RTZ_CUDA(cudaMemcpyAsync(c->bvh_wexp.p, c->h_w.data(), n * sizeof(float), cudaMemcpyHostToDevice, c->stream));
     }
     RTZ_CUDA(cudaStreamSynchronize(c->stream));
     c->bvh_ready = true;

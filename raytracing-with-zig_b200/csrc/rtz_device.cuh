@@ -24,10 +24,11 @@
 //   * the sphere the ray starts on ("self") is intersected with c = |oc|^2 - r^2 := 0, the exact
 //     value, instead of the FP32-rounded one: this removes the self-intersection bias of a
 //     naive FP32 port (SURVEY §7 risk 5) without touching any other sphere;
-//   * RNG is Philox4x32-10 keyed (seed) with counter (pixel, sample, bounce, block) instead of
-//     one shared sequential Xoshiro stream (north_star); unit vectors come from Marsaglia's
-//     disk method (2 uniforms / attempt, accept pi/4) instead of cube rejection (accept pi/6):
-//     same uniform distribution on the sphere, fewer divergent retries.
+//   * RNG is Philox4x32-10 keyed (seed) with counter (pixel, sample, bounce, 0) instead of
+//     one shared sequential Xoshiro stream (north_star); unit vectors and lens points are drawn in
+//     CLOSED FORM (z uniform + angle; sqrt(u) + angle; sine / cosine from FP32 minimax polynomials)
+//     instead of the reference's rejection loops (accept pi/6 and pi/4): same uniform distributions,
+//     no data-dependent loop, exactly one Philox block per camera ray and per scatter.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -68,41 +69,52 @@ __device__ __forceinline__ uint4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_
 
 // uniform in [0,1): top 24 bits, exact in FP32
 __device__ __forceinline__ float u01(uint32_t x) { return (float)(x >> 8) * 0x1p-24f; }
-// uniform in [-1,1)
-__device__ __forceinline__ float u11(uint32_t x) { return fmaf(2.0f, u01(x), -1.0f); }
 
 struct RngKey {
     uint32_t k0, k1, pixel, sample;
 };
 
-// Point of the unit disk by rejection, two attempts per Philox block (blocks blk0, blk0+1, ...).
-__device__ __forceinline__ void sample_disk(const RngKey& k, uint32_t bounce, uint4 first, bool use_zw_of_first,
-                                            float& a, float& b, float& s) {
-    // `first` is block 0 of the stream; when use_zw_of_first only its .z/.w are free (the camera
-    // used .x/.y for the pixel jitter).
-    uint4 r = first;
-    uint32_t blk = 0;
-    if (!use_zw_of_first) {
-        a = u11(r.x), b = u11(r.y), s = fmaf(b, b, a * a);
-        if (s < 1.0f) return;
-    }
-    for (;;) {
-        a = u11(r.z), b = u11(r.w), s = fmaf(b, b, a * a);
-        if (s < 1.0f) return;
-        r = philox4x32_10(k.pixel, k.sample, bounce, ++blk, k.k0, k.k1);
-        a = u11(r.x), b = u11(r.y), s = fmaf(b, b, a * a);
-        if (s < 1.0f) return;
-    }
+// (cos 2*pi*u, sin 2*pi*u) for the 24-bit uniform u = (x >> 8) * 2^-24.  The top two bits of u pick the quarter
+// turn exactly; the other 22 are the fraction f of that quarter, and sin(pi/2 f) = f S(f^2), cos(pi/2 f) = C(f^2)
+// with degree-4 minimax polynomials (|error| < 2e-7, measured over all 2^22 arguments).  Only IEEE multiplies and
+// explicit fmaf: the CPU mirror reproduces it bit for bit, and there is no rejection loop — every sample costs
+// the same instructions in every lane, and a camera ray / a scatter consumes exactly ONE Philox block.
+__device__ __forceinline__ void cos_sin_2pi(uint32_t x, float& c, float& s) {
+    const uint32_t q = x >> 30;
+    const float f = (float)((x >> 8) & 0x3FFFFFu) * 0x1p-22f;
+    const float z = f * f;
+    float sp = fmaf(z, 0x1.3e7abap-13f, -0x1.3259fap-8f);
+    sp = fmaf(z, sp, 0x1.46693cp-4f);
+    sp = fmaf(z, sp, -0x1.4abbc6p-1f);
+    sp = fmaf(z, sp, 0x1.921fb6p+0f);
+    sp = sp * f;
+    float cp = fmaf(z, 0x1.c29b9cp-11f, -0x1.550192p-6f);
+    cp = fmaf(z, cp, 0x1.03bd86p-2f);
+    cp = fmaf(z, cp, -0x1.3bd3aep+0f);
+    cp = fmaf(z, cp, 1.0f);
+    const float a = (q & 1u) ? sp : cp;  // |cos|, |sin| after q quarter turns
+    const float b = (q & 1u) ? cp : sp;
+    c = (q == 1u || q == 2u) ? -a : a;
+    s = (q >= 2u) ? -b : b;
 }
 
-// Vec.randomUnitVec (src/vec.zig:71-80): uniform on the unit sphere.  Marsaglia (1972):
-// (a,b) uniform in the disk, s = a^2+b^2  ->  (2a sqrt(1-s), 2b sqrt(1-s), 1-2s).
-__device__ __forceinline__ void random_unit_vec(const RngKey& k, uint32_t bounce, uint4 block0, float& ux,
-                                                float& uy, float& uz) {
-    float a, b, s;
-    sample_disk(k, bounce, block0, false, a, b, s);
-    const float q = 2.0f * sqrtf(1.0f - s);
-    ux = a * q, uy = b * q, uz = fmaf(-2.0f, s, 1.0f);
+// Vec.randomInUnitDisk (src/vec.zig:82-92): uniform in the unit disk.  The reference rejects from the square;
+// here the same distribution in closed form: radius sqrt(u1), angle 2*pi*u2.
+__device__ __forceinline__ void sample_disk(uint32_t x1, uint32_t x2, float& a, float& b) {
+    const float rad = sqrtf(u01(x1));
+    float c, s;
+    cos_sin_2pi(x2, c, s);
+    a = rad * c, b = rad * s;
+}
+
+// Vec.randomUnitVec (src/vec.zig:71-80): uniform on the unit sphere.  The reference rejects from the cube and
+// normalises; here the same distribution in closed form (Archimedes): z uniform in (-1, 1], angle 2*pi*u2.
+__device__ __forceinline__ void random_unit_vec(uint32_t x1, uint32_t x2, float& ux, float& uy, float& uz) {
+    const float z = fmaf(-2.0f, u01(x1), 1.0f);
+    const float rad = sqrtf(fmaf(-z, z, 1.0f));
+    float c, s;
+    cos_sin_2pi(x2, c, s);
+    ux = rad * c, uy = rad * s, uz = z;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -136,8 +148,8 @@ __device__ __forceinline__ void camera_ray(const DevCamera& c, const RngKey& k, 
     const float psz = fmaf(c.dvz, sy, fmaf(c.duz, sx, c.p0z));
     p.ox = c.cx, p.oy = c.cy, p.oz = c.cz;
     if (c.defocus) {  // defocusDiskSample (:212-215)
-        float a, b, s;
-        sample_disk(k, 0u, r, true, a, b, s);
+        float a, b;
+        sample_disk(r.z, r.w, a, b);
         p.ox = fmaf(c.vvx, b, fmaf(c.uux, a, c.cx));
         p.oy = fmaf(c.vvy, b, fmaf(c.uuy, a, c.cy));
         p.oz = fmaf(c.vvz, b, fmaf(c.uuz, a, c.cz));
@@ -271,7 +283,7 @@ __device__ __forceinline__ bool shade(const DevCamera& cam, const RngKey& k, con
         }
     } else {
         float ux, uy, uz;
-        random_unit_vec(k, stream, r0, ux, uy, uz);
+        random_unit_vec(r0.y, r0.z, ux, uy, uz);
         if (type == kLambertian) {
             // Lambertian.scatter (src/material.zig:27-39) incl. nearZero WITHOUT abs (Q1)
             ndx = nx + ux, ndy = ny + uy, ndz = nz + uz;

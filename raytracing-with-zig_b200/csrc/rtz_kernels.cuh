@@ -24,20 +24,37 @@ struct TraceParams {
     const float4* geom;     // [n_pad]   per-lane lookups: {cx, cy, cz, -r^2}
     const float4* aux;      // [n_pad] {r, 1/r, fuzz|ior, type}
     const float4* albedo;   // [n_pad] {r,g,b,1/ior}
+    const float* wexp;      // [n_pad] w of the pair layout as a plain row (per-lane lookups: coop_hit, the BVH extension)
     int n_spheres;
     int n_pad;              // n rounded up to a multiple of 8 (padding spheres can never be hit)
-    uint32_t chunk;         // samples per work chunk
+    // Work chunks, handed out by the global queue in index order.  The frame's first `tail_first_pixel` local
+    // pixels are cut into runs of `chunk` samples of ONE pixel (a warp's 64 paths then share their camera
+    // geometry).  The remaining pixels — the END of the queue — are cut the other way: a chunk is ONE sample
+    // index of `tail_width` consecutive pixels.  Small chunks make all warps run dry within a few microseconds
+    // of each other, and cutting across pixels spreads the samples of an expensive pixel (paths trapped inside
+    // a glass sphere: 4x the bounces, measured with RTZ_TIMELINE) over many warps instead of leaving one warp
+    // with 64 deep paths after everybody else has finished.
+    uint32_t chunk;         // samples per work chunk (body of the queue)
     uint32_t chunks_per_pixel;
-    uint64_t n_chunks;      // n_local_pixels(padded) * chunks_per_pixel
+    uint32_t tail_width;    // pixels per chunk at the end of the queue
+    uint32_t tail_blocks;   // chunks per sample index there: ceil(tail pixels / tail_width)
+    uint32_t tail_first_pixel;  // first local pixel of the tail region
+    uint32_t n_local_pixels;
+    const uint32_t* order;  // queue position q -> local pixel, or null for the identity.  Written by classify_kernel:
+                            // pixels whose centre ray enters glass come FIRST (their paths are 4x as long: longest
+                            // processing time first, so that no warp is left with an expensive pixel at the end)
+    uint32_t coop_max;      // queue drained and at most this many live paths in the warp: sphere-parallel sweep
+    uint64_t n_body_chunks; // tail_first_pixel * chunks_per_pixel
+    uint64_t n_chunks;      // n_body_chunks + tail_blocks * spp
     unsigned long long* accum;    // [n_local_pixels*3] 32.32 fixed-point colour sums
     unsigned long long* counter;  // work-queue head
     unsigned long long* stats;    // {samples, segments, depth_capped, absorbed, (BVH tests), NaN samples}
+    unsigned long long* timeline; // diagnostics (RTZ_TIMELINE=1), else null: per warp {start, queue ran dry, done} in ns, {lockstep, sphere-parallel} iterations after it ran dry, SM id
 };
 
 // Scenes of up to kMaxConstSpheres spheres travel as a __grid_constant__ kernel parameter: the
 // sweep then reads them through the constant bank with uniform loads (LDCU -> uniform registers
 // -> UR operands of FADD2/FFMA2), which needs no LDS, no vector registers and no shared memory.
-constexpr int kConstDefer = 8;          // constant-bank kernel: candidates are resolved every 8 blocks (256 spheres)
 constexpr int kMaxConstSpheres = 512;  // 8 KiB: what the constant cache serves at full rate (1024 spheres already thrash it: measured)
 struct TraceParamsConst {
     TraceParams p;
@@ -154,29 +171,19 @@ __device__ __forceinline__ void test_pair(const float4 p0, const float4 p1, cons
 // n_pad is a multiple of 8; padding spheres have w = -inf -> disc = -inf -> never a candidate.
 // kConstBank selects two register-allocation nudges that were measured per kernel (same arithmetic):
 // the constant-bank kernel pins 2*o (+0.8 %), the shared-memory kernel forms t_min*len late (+4 % at N = 1024).
-//
-// kDefer > 0: DEFERRED candidate resolution.  Resolving a block's candidates right behind its 32 tests makes
-// the warp enter a divergent region 16 times per sweep at N = 485 (some lane nearly always has a candidate,
-// ~9 of 32 lanes active: 9 % of the kernel's warp-instructions).  Instead every lane appends the block's
-// (mask, base) to a private list in shared memory — one unconditional store, the count advances only for a
-// non-empty mask, no branch — and the lists are resolved every kDefer blocks: the divergent region is entered
-// n_blocks / kDefer times, and inside it every lane walks ITS OWN candidates, so the warp pays the maximum
-// over the lanes of their candidate counts, not their sum over the blocks.  The candidates of a path are
-// still evaluated in ascending sphere order with the same shrinking t_max: same arithmetic, same image.
-// `defer` = [2 slots][kDefer entries][kBlock threads] uint2, bank = thread: conflict-free.
-template <bool kConstBank, int kDefer, int kBlock>
+// (Deferring the candidates of several blocks to per-lane lists and resolving them together was built twice and
+// measured on one box: +3.7 % warp-instructions, +0.4 % time.  The 64 paths of a warp come from one pixel, so
+// their candidates coincide and one pass per non-empty block already serves all lanes.)
+template <bool kConstBank>
 __device__ __forceinline__ void sweep2(const float4* __restrict__ pairs, const float4* __restrict__ gather, int n_pad,
                                        float tmin, float tmax, const Path& a, const Path& b, float& ta, int& ia,
-                                       float& tb, int& ib, uint2* __restrict__ defer) {
+                                       float& tb, int& ib) {
     RayK ka = ray_constants(a), kb = ray_constants(b);
     // pin 2*o in registers: left alone, ptxas keeps o and re-adds it for every block of 32 spheres
     if (kConstBank) asm volatile("" : "+f"(ka.tx), "+f"(ka.ty), "+f"(ka.tz), "+f"(kb.tx), "+f"(kb.ty), "+f"(kb.tz));
     // Interval(t_min, t_max) of Scene.interval in distance units (directions are unit length)
     float ca = tmax * a.len, cb = tmax * b.len;
     int ba = -1, bb = -1;
-    uint2* const list_a = defer + threadIdx.x;                     // entry e: list_a[e * kBlock]
-    uint2* const list_b = defer + kDefer * kBlock + threadIdx.x;
-    int na = 0, nb = 0, pending = 0;
     for (int base = 0; base < n_pad; base += 32) {
         const int cnt = min(32, n_pad - base);
         unsigned ma = 0xFFFFFFFFu, mb = 0xFFFFFFFFu;  // 1 = miss
@@ -191,25 +198,7 @@ __device__ __forceinline__ void sweep2(const float4* __restrict__ pairs, const f
             }
         }
         const unsigned canda = ~ma, candb = ~mb;
-        if (kDefer > 0) {
-            list_a[na * kBlock] = make_uint2(canda, (unsigned)base);
-            list_b[nb * kBlock] = make_uint2(candb, (unsigned)base);
-            na += canda != 0u, nb += candb != 0u;
-            if (++pending < kDefer && base + 32 < n_pad) continue;  // warp-uniform
-            pending = 0;
-            float la = a.len, lb = b.len;
-            if (!kConstBank) asm volatile("" : "+f"(la), "+f"(lb));
-            for (int e = 0; e < na; ++e) {
-                const uint2 v = list_a[e * kBlock];
-                resolve_candidates(gather, v.x, (int)v.y, min(32, n_pad - (int)v.y), a, tmin * la, ca, ba);
-            }
-            for (int e = 0; e < nb; ++e) {
-                const uint2 v = list_b[e * kBlock];
-                resolve_candidates(gather, v.x, (int)v.y, min(32, n_pad - (int)v.y), b, tmin * lb, cb, bb);
-            }
-            na = nb = 0;
-            __syncwarp();  // reconverge before the next block's uniform sweep
-        } else if (canda | candb) {
+        if (canda | candb) {
             // t_min * len is formed HERE, behind an opaque copy, so that it does not occupy two more
             // registers across the whole sweep of the shared-memory kernel (96 registers at 5 CTAs per SM)
             float la = a.len, lb = b.len;
@@ -241,11 +230,129 @@ __device__ __forceinline__ void finish_or_continue(const TraceParams& P, const f
     }
 }
 
+// The same for trace_body, which keeps no per-lane work counters (every register counts at 80 per thread):
+// segments and samples are counted per warp from the live-slot votes, the two rare endings go straight to global
+// memory.
+__device__ __forceinline__ void finish_or_continue(const TraceParams& P, const float4* gather, const float4* s_aux,
+                                                   const float4* s_alb, Slot& s, float t, int best) {
+    float sr, sg, sb;
+    int term;
+    if (shade(P.cam, s.key, gather, s_aux, s_alb, s.path, t, best, sr, sg, sb, term)) {
+        const unsigned long long fr = to_fixed(sr), fg = to_fixed(sg), fb = to_fixed(sb);
+        unsigned long long* px = P.accum + 3ull * s.lp;
+        if (fr) atomicAdd(px + 0, fr);
+        if (fg) atomicAdd(px + 1, fg);
+        if (fb) atomicAdd(px + 2, fb);
+        if (sr != sr || sg != sg || sb != sb) atomicAdd(P.stats + 5, 1ULL);  // NaN sample: adds 0, but is counted
+        if (term == 2) atomicAdd(P.stats + 2, 1ULL);  // depth cap: 0.02 % of the samples
+        if (term == 1) atomicAdd(P.stats + 3, 1ULL);  // absorbed by a metal: 0.2 %
+        s.alive = false;
+    }
+}
+
 // The body shared by the two kernels below.  `geo` is the warp-uniform geometry the sweep reads,
 // `gather` the copy for per-lane lookups (candidate roots, hit records).
-template <bool kConstBank, int kDefer, int kBlock>
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+
+// One chunk of work (warp-uniform), in queue positions q (local pixel = queue_pixel(q)).
+// across == false: samples [next, end) of position q0.  across == true: sample `sample` of positions q0 + [next, end).
+struct Chunk {
+    uint32_t q0 = 0, next = 0, end = 0, sample = 0;
+    bool across = false;
+};
+__device__ __forceinline__ uint32_t queue_pixel(const TraceParams& P, uint32_t q) {
+    return P.order ? __ldg(P.order + q) : q;
+}
+__device__ __forceinline__ void decode_chunk(const TraceParams& P, unsigned long long cid, uint32_t spp, Chunk& c) {
+    if (cid < P.n_body_chunks) {
+        c.q0 = (uint32_t)(cid / P.chunks_per_pixel);
+        const uint32_t part = (uint32_t)(cid - (unsigned long long)c.q0 * P.chunks_per_pixel);
+        c.next = part * P.chunk;
+        c.end = min(c.next + P.chunk, spp);
+        c.sample = 0u, c.across = false;
+    } else {
+        cid -= P.n_body_chunks;
+        c.sample = (uint32_t)(cid / P.tail_blocks);
+        const uint32_t blk = (uint32_t)(cid - (unsigned long long)c.sample * P.tail_blocks);
+        c.q0 = P.tail_first_pixel + blk * P.tail_width;
+        c.next = 0u;
+        c.end = min(P.tail_width, P.n_local_pixels - c.q0);
+        c.across = true;
+    }
+}
+
+// HittableList.hit for ONE path by the whole warp: lane l tests spheres l, l + 32, ... with the arithmetic of the
+// sweep (sign of the expanded discriminant, then the direct-form root, ascending within the lane), and the
+// closest hit is the warp's minimum over (t, sphere index).  That is the hit of the ascending loop: a sphere is
+// accepted iff its root beats every earlier one strictly, so the winner is the smallest t and, among equal t, the
+// smallest index — independent of how the spheres are dealt to the lanes (the BVH extension relies on the same
+// fact).  Used while the queue drains: a warp that is down to a few live paths would otherwise sweep all N
+// spheres with 64 slots for them, 6.5 us per bounce on an empty SM (measured with RTZ_TIMELINE: the last 1 % of
+// the warps used to finish 0.4 ms after the other 99 %).  The discriminants of 8 spheres per lane are evaluated
+// back to back so that their loads overlap (the rows are cold in L1: the sweep reads the constant bank).
+__device__ __forceinline__ void coop_hit(const float4* __restrict__ geom, const float* __restrict__ wexp, int n,
+                                         float tmin, float tmax, const Path& mine, int src, unsigned lane, float& t_out,
+                                         int& best_out) {
+    Path q;
+    q.ox = __shfl_sync(0xFFFFFFFFu, mine.ox, src), q.oy = __shfl_sync(0xFFFFFFFFu, mine.oy, src);
+    q.oz = __shfl_sync(0xFFFFFFFFu, mine.oz, src), q.dx = __shfl_sync(0xFFFFFFFFu, mine.dx, src);
+    q.dy = __shfl_sync(0xFFFFFFFFu, mine.dy, src), q.dz = __shfl_sync(0xFFFFFFFFu, mine.dz, src);
+    q.len = __shfl_sync(0xFFFFFFFFu, mine.len, src), q.self = __shfl_sync(0xFFFFFFFFu, mine.self, src);
+    const float tmin_d = tmin * q.len;
+    float closest = tmax * q.len;
+    int best = -1;
+    const RayK k = ray_constants(q);
+    for (int base = (int)lane; base < n; base += 256) {  // 8 spheres per lane and round
+        unsigned cand = 0u;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int i = base + 32 * j;
+            if (i < n) {
+                const float4 g = __ldg(geom + i);
+                const float d = expanded_disc(g.x, g.y, g.z, __ldg(wexp + i), q, k);
+                cand |= (__float_as_uint(d) >> 31 ^ 1u) << j;
+            }
+        }
+        while (cand) {  // ascending
+            const int j = __ffs(cand) - 1;
+            cand &= cand - 1u;
+            const int i = base + 32 * j;
+            const float4 g = __ldg(geom + i);
+            candidate_root(g, g.w, i, q, tmin_d, closest, best);
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const float t2 = __shfl_xor_sync(0xFFFFFFFFu, closest, o);
+        const int b2 = __shfl_xor_sync(0xFFFFFFFFu, best, o);
+        if (t2 < closest || (t2 == closest && (unsigned)b2 < (unsigned)best)) closest = t2, best = b2;  // -1 = none
+    }
+    if ((int)lane == src) t_out = closest, best_out = best;
+}
+
+// a staged camera ray (trace_body's warp-cooperative regeneration): origin, unit direction, |direction|
+__device__ __forceinline__ void take_camera_ray(const float* stage, uint32_t j, Path& p) {
+    p.ox = stage[0 * 64 + j], p.oy = stage[1 * 64 + j], p.oz = stage[2 * 64 + j];
+    p.dx = stage[3 * 64 + j], p.dy = stage[4 * 64 + j], p.dz = stage[5 * 64 + j];
+    p.len = stage[6 * 64 + j];
+    p.tr = p.tg = p.tb = 1.0f;
+    p.self = -1;
+    p.bounce = 0;
+}
+constexpr int kStageFloats = 9 * 64;  // per warp: 9 rows (ray, |direction|, pixel id, local pixel) of 64 rays (two slots per lane)
+
+template <bool kConstBank, int kBlock>
 __device__ __forceinline__ void trace_body(const TraceParams& P, const float4* __restrict__ pairs,
-                                           const float4* __restrict__ gather, uint2* __restrict__ defer) {
+                                           const float4* __restrict__ gather, float* __restrict__ stage_mem) {
+    float* const stage = stage_mem + (threadIdx.x >> 5) * kStageFloats;
+    uint32_t* const stage_u = reinterpret_cast<uint32_t*>(stage);
+    unsigned long long* const tl =
+        P.timeline ? P.timeline + 6ull * ((unsigned long long)blockIdx.x * (kBlock / 32) + (threadIdx.x >> 5)) : nullptr;
+    if (tl && (threadIdx.x & 31u) == 0u) tl[0] = globaltimer_ns();
     // material rows are touched once per HIT (not per test): they stay in global memory / L1
     const float4* s_aux = P.aux;
     const float4* s_alb = P.albedo;
@@ -261,19 +368,24 @@ __device__ __forceinline__ void trace_body(const TraceParams& P, const float4* _
     A.path.tr = A.path.tg = A.path.tb = 0.f, A.path.len = 1.f, A.path.self = -1, A.path.bounce = 0;
     B.path = A.path;
 
-    // warp-uniform chunk state
-    uint32_t ch_lp = 0, ch_x = 0, ch_y = 0, ch_next = 0, ch_end = 0;
+    // warp-uniform chunk state (parking it in shared memory between regenerations was tried: ptxas then no longer
+    // treats the branches on it as uniform and the sweep leaves the uniform datapath)
     bool exhausted = false;
+    Chunk ch;
+    uint32_t ch_lp = 0, ch_x = 0, ch_y = 0;  // the pixel of a one-pixel chunk
 
+    // work counters, per warp, from the votes: a slot that was live and is free now has finished a sample
     unsigned long long n_seg = 0;
-    uint32_t n_samp = 0, n_cap = 0, n_abs = 0;
+    uint32_t n_samp = 0;
+    unsigned prev_a = 0u, prev_b = 0u;
 
     for (;;) {
         unsigned need_a = __ballot_sync(0xFFFFFFFFu, !A.alive);
         unsigned need_b = __ballot_sync(0xFFFFFFFFu, !B.alive);
+        n_samp += __popc(prev_a & need_a) + __popc(prev_b & need_b);
         if (need_a | need_b) {
             while ((need_a | need_b) && !exhausted) {
-                if (ch_next >= ch_end) {
+                if (ch.next >= ch.end) {
                     unsigned long long cid = 0;
                     if (lane == 0) cid = atomicAdd(P.counter, 1ULL);
                     cid = __shfl_sync(0xFFFFFFFFu, cid, 0);
@@ -281,62 +393,112 @@ __device__ __forceinline__ void trace_body(const TraceParams& P, const float4* _
                     // visible to ptxas (uniform branches keep the warp provably converged)
                     if (__any_sync(0xFFFFFFFFu, cid >= P.n_chunks)) {
                         exhausted = true;
+                        if (tl && lane == 0u) tl[1] = globaltimer_ns();
                         break;
                     }
-                    ch_lp = (uint32_t)(cid / P.chunks_per_pixel);
-                    const uint32_t part = (uint32_t)(cid - (unsigned long long)ch_lp * P.chunks_per_pixel);
-                    const bool inside = local_to_global(P.sh, cam.width, cam.height, ch_lp, ch_x, ch_y);
-                    if (__any_sync(0xFFFFFFFFu, !inside)) continue;  // tile padding
-                    ch_next = part * P.chunk;
-                    ch_end = min(ch_next + P.chunk, cam.spp);
+                    // (decoded into a temporary and committed only behind the `continue`: written the other way
+                    // round ptxas no longer proves the loop converged and the sweep leaves the uniform datapath)
+                    Chunk c;
+                    decode_chunk(P, cid, cam.spp, c);
+                    uint32_t x = 0, y = 0;
+                    const uint32_t lp = c.across ? 0u : queue_pixel(P, c.q0);
+                    const bool padding = !c.across && !local_to_global(P.sh, cam.width, cam.height, lp, x, y);
+                    if (__any_sync(0xFFFFFFFFu, padding)) continue;  // a one-pixel chunk of tile padding
+                    ch = c, ch_lp = lp, ch_x = x, ch_y = y;
                 }
-                const uint32_t avail = ch_end - ch_next;
+                const bool across = __any_sync(0xFFFFFFFFu, ch.across);
+                const uint32_t avail = ch.end - ch.next;
                 const uint32_t na = __popc(need_a);
                 const uint32_t rank_a = __popc(need_a & lt_mask);
                 const uint32_t rank_b = na + __popc(need_b & lt_mask);
-                if (((need_a >> lane) & 1u) && rank_a < avail) {
-                    A.lp = ch_lp;
-                    A.key.pixel = ch_y * cam.width + ch_x, A.key.sample = ch_next + rank_a;
-                    camera_ray(cam, A.key, ch_x, ch_y, A.path);
-                    A.alive = true;
+                const uint32_t n_gen = min(na + (uint32_t)__popc(need_b), avail);
+                // Camera rays, warp-cooperative: the chunk's next n_gen rays are generated 32 at a time by ALL
+                // lanes into the warp's staging rows and then picked up by the lanes that own the free slots.
+                // Which lane computes a ray does not matter — its random numbers depend on (pixel, sample) only —
+                // and one full-width pass replaces two passes of ~7 active lanes each (ncu: 28 % of the kernel's
+                // warp-instructions at 16 spheres, profiles/r2_*).
+                for (uint32_t j0 = 0; j0 < n_gen; j0 += 32u) {
+                    const uint32_t j = j0 + lane;
+                    if (j < n_gen) {
+                        uint32_t x = ch_x, y = ch_y, sample = ch.next + j, lp = ch_lp;
+                        bool inside = true;
+                        if (across) {
+                            lp = queue_pixel(P, ch.q0 + ch.next + j);
+                            inside = local_to_global(P.sh, cam.width, cam.height, lp, x, y);
+                            sample = ch.sample;
+                        }
+                        const uint32_t pix = y * cam.width + x;
+                        stage_u[7 * 64 + j] = inside ? pix : 0xFFFFFFFFu;  // tile padding: no ray
+                        stage_u[8 * 64 + j] = lp;
+                        if (inside) {
+                            const RngKey key{cam.key0, cam.key1, pix, sample};
+                            Path t;
+                            camera_ray(cam, key, x, y, t);
+                            stage[0 * 64 + j] = t.ox, stage[1 * 64 + j] = t.oy, stage[2 * 64 + j] = t.oz;
+                            stage[3 * 64 + j] = t.dx, stage[4 * 64 + j] = t.dy, stage[5 * 64 + j] = t.dz;
+                            stage[6 * 64 + j] = t.len;
+                        }
+                    }
                 }
-                if (((need_b >> lane) & 1u) && rank_b < avail) {
-                    B.lp = ch_lp;
-                    B.key.pixel = ch_y * cam.width + ch_x, B.key.sample = ch_next + rank_b;
-                    camera_ray(cam, B.key, ch_x, ch_y, B.path);
-                    B.alive = true;
+                __syncwarp();
+                if (((need_a >> lane) & 1u) && rank_a < n_gen) {
+                    const uint32_t pix = stage_u[7 * 64 + rank_a];
+                    if (pix != 0xFFFFFFFFu) {
+                        A.lp = stage_u[8 * 64 + rank_a];
+                        A.key.pixel = pix, A.key.sample = across ? ch.sample : ch.next + rank_a;
+                        take_camera_ray(stage, rank_a, A.path);
+                        A.alive = true;
+                    }
                 }
-                ch_next += min(na + (uint32_t)__popc(need_b), avail);
+                if (((need_b >> lane) & 1u) && rank_b < n_gen) {
+                    const uint32_t pix = stage_u[7 * 64 + rank_b];
+                    if (pix != 0xFFFFFFFFu) {
+                        B.lp = stage_u[8 * 64 + rank_b];
+                        B.key.pixel = pix, B.key.sample = across ? ch.sample : ch.next + rank_b;
+                        take_camera_ray(stage, rank_b, B.path);
+                        B.alive = true;
+                    }
+                }
+                __syncwarp();  // the rows are rewritten by the next round
+                ch.next += n_gen;
                 need_a = __ballot_sync(0xFFFFFFFFu, !A.alive);
                 need_b = __ballot_sync(0xFFFFFFFFu, !B.alive);
             }
+
         }
         // loop exit on a FRESH warp vote: the condition is warp-uniform by construction, which lets
         // ptxas keep the sweep below on the uniform datapath (uniform loads / UR operands)
-        if (__ballot_sync(0xFFFFFFFFu, A.alive || B.alive) == 0u) break;  // queue drained, every path finished
-        float ta, tb;
-        int ia, ib;
-        sweep2<kConstBank, kDefer, kBlock>(pairs, gather, P.n_pad, cam.tmin, cam.tmax, A.path, B.path, ta, ia, tb, ib, defer);
-        if (A.alive) finish_or_continue(P, gather, s_aux, s_alb, A, ta, ia, n_seg, n_samp, n_cap, n_abs);
-        if (B.alive) finish_or_continue(P, gather, s_aux, s_alb, B, tb, ib, n_seg, n_samp, n_cap, n_abs);
+        const unsigned live_a = __ballot_sync(0xFFFFFFFFu, A.alive), live_b = __ballot_sync(0xFFFFFFFFu, B.alive);
+        if ((live_a | live_b) == 0u) break;  // queue drained, every path finished
+        n_seg += (unsigned)(__popc(live_a) + __popc(live_b));
+        prev_a = live_a, prev_b = live_b;
+        float ta = 0.f, tb = 0.f;
+        int ia = -1, ib = -1;
+        const bool coop = exhausted && (uint32_t)(__popc(live_a) + __popc(live_b)) <= P.coop_max;
+        if (tl && exhausted && lane == 0u) tl[coop ? 4 : 3] += 1ull;
+        if (coop) {
+            // the tail of the frame: a handful of long paths left in the warp -> one path at a time, spheres across lanes
+            for (unsigned m = live_a; m; m &= m - 1u)
+                coop_hit(P.geom, P.wexp, P.n_spheres, cam.tmin, cam.tmax, A.path, __ffs(m) - 1, lane, ta, ia);
+            for (unsigned m = live_b; m; m &= m - 1u)
+                coop_hit(P.geom, P.wexp, P.n_spheres, cam.tmin, cam.tmax, B.path, __ffs(m) - 1, lane, tb, ib);
+        } else {
+            sweep2<kConstBank>(pairs, gather, P.n_pad, cam.tmin, cam.tmax, A.path, B.path, ta, ia, tb, ib);
+        }
+        if (A.alive) finish_or_continue(P, gather, s_aux, s_alb, A, ta, ia);
+        if (B.alive) finish_or_continue(P, gather, s_aux, s_alb, B, tb, ib);
         // explicit reconvergence point: with it ptxas proves the loop top converged (no BRA.DIV before
         // the votes) and keeps the sweep's addressing / constant-bank operands on the uniform datapath
         __syncwarp();
     }
-    // warp-reduce the work counters, one atomic per warp and counter
-    unsigned long long v0 = n_samp, v1 = n_seg, v2 = n_cap, v3 = n_abs;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        v0 += __shfl_xor_sync(0xFFFFFFFFu, v0, o);
-        v1 += __shfl_xor_sync(0xFFFFFFFFu, v1, o);
-        v2 += __shfl_xor_sync(0xFFFFFFFFu, v2, o);
-        v3 += __shfl_xor_sync(0xFFFFFFFFu, v3, o);
+    if (tl && lane == 0u) {
+        unsigned smid;
+        asm volatile("mov.u32 %0, %smid;" : "=r"(smid));
+        tl[2] = globaltimer_ns(), tl[5] = smid;
     }
-    if (lane == 0) {
-        atomicAdd(P.stats + 0, v0);
-        atomicAdd(P.stats + 1, v1);
-        atomicAdd(P.stats + 2, v2);
-        atomicAdd(P.stats + 3, v3);
+    if (lane == 0u) {  // one atomic per warp and counter
+        atomicAdd(P.stats + 0, (unsigned long long)n_samp);
+        atomicAdd(P.stats + 1, n_seg);
     }
 }
 
@@ -453,12 +615,12 @@ __device__ __forceinline__ void trace_body_parked(const TraceParams& P, const fl
                     exhausted = true;
                     break;
                 }
-                ch_lp = (uint32_t)(cid / P.chunks_per_pixel);
-                const uint32_t part = (uint32_t)(cid - (unsigned long long)ch_lp * P.chunks_per_pixel);
+                Chunk c;  // this kernel is launched without a tail region: every chunk is a run of one pixel
+                decode_chunk(P, cid, cam.spp, c);
+                ch_lp = queue_pixel(P, c.q0);
                 const bool inside = local_to_global(P.sh, cam.width, cam.height, ch_lp, ch_x, ch_y);
                 if (__any_sync(0xFFFFFFFFu, !inside)) continue;  // tile padding
-                ch_next = part * P.chunk;
-                ch_end = min(ch_next + P.chunk, cam.spp);
+                ch_next = c.next, ch_end = c.end;
             }
             const uint32_t n = min(total, ch_end - ch_next);
             uint32_t before = 0;
@@ -596,13 +758,8 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks) trace_kernel_const_parked(
 // no register-file bandwidth, which is what bounds FFMA2 on sm_100.  No shared memory at all.
 template <int kBlock, int kMinBlocks>
 __global__ void __launch_bounds__(kBlock, kMinBlocks) trace_kernel_const(const __grid_constant__ TraceParamsConst C) {
-    __shared__ uint2 defer[2 * kConstDefer * kBlock];  // 16 KiB at 128 threads
-    trace_body<true, kConstDefer, kBlock>(C.p, C.pairs, C.p.geom, defer);
-}
-// the same kernel resolving every block's candidates at once (RTZ_VARIANT=5: A/B of the deferred lists)
-template <int kBlock, int kMinBlocks>
-__global__ void __launch_bounds__(kBlock, kMinBlocks) trace_kernel_const_nodefer(const __grid_constant__ TraceParamsConst C) {
-    trace_body<true, 0, kBlock>(C.p, C.pairs, C.p.geom, nullptr);
+    __shared__ float stage[(kBlock / 32) * kStageFloats];
+    trace_body<true, kBlock>(C.p, C.pairs, C.p.geom, stage);
 }
 
 // K1b: geometry staged into shared memory by 1-D TMA bulk copies (cp.async.bulk + mbarrier): scenes
@@ -613,6 +770,7 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks) trace_kernel_smem(const __
     float4* s_pairs = reinterpret_cast<float4*>(smem_raw);  // [n_pad] sweep layout
     float4* s_geom = s_pairs + P.n_pad;                      // [n_pad] per-lane lookups
     __shared__ __align__(8) uint64_t s_bar;
+    __shared__ float stage[(kBlock / 32) * kStageFloats];
     if (threadIdx.x == 0) {
         mbar_init(&s_bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -625,7 +783,7 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks) trace_kernel_smem(const __
         bulk_g2s(s_geom, P.geom, bytes, &s_bar);
     }
     mbar_wait(&s_bar, 0);
-    trace_body<false, 0, kBlock>(P, s_pairs, s_geom, nullptr);
+    trace_body<false, kBlock>(P, s_pairs, s_geom, stage);
 }
 
 // K1c: geometry read from global memory (L1 / L2, warp-uniform addresses): scenes whose 32 B per sphere do
@@ -633,7 +791,36 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks) trace_kernel_smem(const __
 // limit (src/hittable.zig:43-62), so neither has the drop-in; the sweep just loses its staging.
 template <int kBlock, int kMinBlocks>
 __global__ void __launch_bounds__(kBlock, kMinBlocks) trace_kernel_global(const __grid_constant__ TraceParams P) {
-    trace_body<false, 0, kBlock>(P, P.pairs, P.geom, nullptr);
+    __shared__ float stage[(kBlock / 32) * kStageFloats];
+    trace_body<false, kBlock>(P, P.pairs, P.geom, stage);
+}
+
+// ---------------------------------------------------------------------------------------------
+// K0: queue order.  One thread per local pixel traces the ray through the pixel centre (no jitter, lens centre)
+// to its first hit; pixels that see a dielectric are queued first, all others behind them.  Scheduling only:
+// the image does not depend on the order (tested), the frame's makespan does — a 256-sample chunk of a pixel
+// inside a glass sphere costs 4x a normal one, and whoever picks such a chunk last finishes last.
+// ---------------------------------------------------------------------------------------------
+__global__ void classify_kernel(const __grid_constant__ TraceParams P, uint32_t* __restrict__ order,
+                                unsigned int* __restrict__ cursors) {
+    const uint32_t lp = blockIdx.x * blockDim.x + threadIdx.x;
+    if (lp >= P.n_local_pixels) return;
+    uint32_t x, y;
+    bool hard = false;
+    if (local_to_global(P.sh, P.cam.width, P.cam.height, lp, x, y)) {
+        const DevCamera& c = P.cam;
+        Path p;
+        p.ox = c.cx, p.oy = c.cy, p.oz = c.cz, p.self = -1, p.bounce = 0, p.tr = p.tg = p.tb = 1.f;
+        const float fx = (float)x, fy = (float)y;
+        set_direction(p, fmaf(c.dvx, fy, fmaf(c.dux, fx, c.p0x)) - c.cx, fmaf(c.dvy, fy, fmaf(c.duy, fx, c.p0y)) - c.cy,
+                      fmaf(c.dvz, fy, fmaf(c.duz, fx, c.p0z)) - c.cz);
+        float t;
+        int best;
+        sweep_rows(P.geom, P.pairs, 0, P.n_spheres, p, c.tmin, c.tmax, t, best);
+        hard = best >= 0 && __float_as_int(__ldg(P.aux + best).w) == kDielectric;
+    }
+    const uint32_t pos = hard ? atomicAdd(cursors + 0, 1u) : P.n_local_pixels - 1u - atomicAdd(cursors + 1, 1u);
+    order[pos] = lp;
 }
 
 // ---------------------------------------------------------------------------------------------

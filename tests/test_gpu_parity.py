@@ -119,14 +119,30 @@ def test_final_scene_matches_mirror_bit_exact(pkg, gpu, orc):
 
 def test_image_is_independent_of_the_schedule(pkg, gpu, monkeypatch):
     """Integer accumulation + counter-based RNG: another launch shape, and even another kernel organisation
-    (RTZ_VARIANT=4: four paths per thread, path state parked in shared memory, warp-cooperative camera rays),
-    must give the same bytes and the same work counters."""
+    (RTZ_VARIANT=4: four paths per thread, path state parked in shared memory), must give the same bytes and
+    the same work counters."""
     prng, sp, n = R.final_scene(0xDEADBEEF)
     cam = R.main_camera(160, 24, seed=7)
     gpu.upload(sp, n)
     img0, st0 = gpu.render(cam)
     sh = pkg.rtz_shard(1, 3, 16, 16)
     img0s, st0s = gpu.render(cam, sh)
+    # work-queue shape and the tail's sphere-parallel sweep: chunk sizes, the across-pixel chunks at the end of the
+    # queue (none / every pixel of the frame), the live-path threshold below which a drained warp sweeps one path
+    # with all its lanes (0 = never, 64 = always)
+    for env in ({"RTZ_COOP_MAX": "0"}, {"RTZ_COOP_MAX": "64"}, {"RTZ_CHUNK": "7", "RTZ_TAIL_WIDTH": "1"},
+                {"RTZ_TAIL_WIDTH": "0"}, {"RTZ_TAIL_WIDTH": "64", "RTZ_TAIL_CHUNKS": "100"},
+                {"RTZ_CHUNK": "24", "RTZ_TAIL_WIDTH": "5", "RTZ_TAIL_CHUNKS": "1", "RTZ_COOP_MAX": "40"},
+                {"RTZ_ORDER": "0"}, {"RTZ_ORDER": "0", "RTZ_TAIL_WIDTH": "0", "RTZ_COOP_MAX": "0"}):
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        img, st = gpu.render(cam)
+        assert np.array_equal(img.cpu().numpy(), img0.cpu().numpy()), env
+        assert (st.samples, st.segments, st.depth_capped, st.absorbed) == (st0.samples, st0.segments, st0.depth_capped, st0.absorbed)
+        imgs, sts = gpu.render(cam, sh)
+        assert np.array_equal(imgs.cpu().numpy(), img0s.cpu().numpy()), env
+        for k in env:
+            monkeypatch.delenv(k)
     for variant in ("1", "2", "4"):
         monkeypatch.setenv("RTZ_VARIANT", variant)
         r = pkg.Renderer(0)
