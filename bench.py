@@ -11,10 +11,14 @@ the frame is sharded by interleaved tiles and gathered to rank 0 over NCCL).  `-
 BASELINE config 4 (3840x2160, 2000 spp) instead.
 
 value  = Msamples/s, device-resident: scene already in HBM, image left in HBM, CUDA events on the
-         launching stream, max over ranks.
-e2e    = the same metric through the reference-facing C-ABI call with HOST buffers (rtz_render at
-         N=1; upload + sharded render + NCCL gather + download at N>1), host<->device copies inside
-         the timed region.
+         launching stream (the Renderer's own torch stream), max over ranks.
+e2e    = the same metric through the reference-facing C-ABI call with HOST buffers, host<->device copies
+         inside the timed region: rtz_render at N=1; at N>1 rtz_render_multi called by rank 0 alone — ONE
+         process driving all N GPUs, which is what a Zig / C host does (the other ranks wait on a CPU
+         barrier).  `e2e_torchrun` keeps the one-process-per-GPU path (upload + sharded render + NCCL gather
+         + download) beside it.
+At N>1 the gathered image is compared with a single-GPU render of the same frame (outside the timed
+regions): `image_equals_1gpu` and the frame's sha256 go into the JSON line.
 roofline = FP32 CUDA-core pipe: 17 algorithmic FLOP per ray-sphere test x tests counted
          by the kernel / trace-kernel time measured with CUDA events by the library.
 cpu_baseline = the oracle (CPU port of the reference; the Zig reference cannot be built here) timed on
@@ -173,10 +177,14 @@ def run_ours(args, rank: int, world: int, local_rank: int):
     out = torch.empty((r.shard_pixels(W, H, shard), 3) if shard is not None else (H, W, 3), dtype=torch.uint8, device=dev)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)   # > 126 MB L2
 
+    cpu_group = dist.new_group(backend="gloo") if world > 1 else None   # a barrier that keeps the GPUs idle
+
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
+
+    last = {}
 
     def step_resident():
         """Device-resident step: render this rank's share (+ gather and de-interleave at N>1)."""
@@ -184,28 +192,32 @@ def run_ours(args, rank: int, world: int, local_rank: int):
         if world > 1:
             g = pkg.distributed.gather_tiles(local, world, rank)
             if rank == 0:
-                r.deinterleave(g, W, H, world, *TILE)
+                last["img"] = r.deinterleave(g, W, H, world, *TILE)
+        else:
+            last["img"] = local
         return st
 
-    for _ in range(args.warmup):
-        step_resident()
-    clocks = ClockSampler(local_rank)
-    barrier()
-    clocks.start()
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    stats = []
-    t_wall0 = time.perf_counter()
-    for s, e in ev:
-        flush.fill_(1)                  # flush L2 between timed iterations (untimed)
-        if world > 1:
-            dist.barrier()
-        s.record()
-        stats.append(step_resident())
-        e.record()
-    torch.cuda.synchronize()
-    t_wall = time.perf_counter() - t_wall0
-    clk = clocks.stop()
-    barrier()
+    # everything below is enqueued on the stream the library launches on, so the CUDA events bracket its kernels
+    with torch.cuda.stream(r.stream):
+        for _ in range(args.warmup):
+            step_resident()
+        clocks = ClockSampler(local_rank)
+        barrier()
+        clocks.start()
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+        stats = []
+        t_wall0 = time.perf_counter()
+        for s, e in ev:
+            flush.fill_(1)                  # flush L2 between timed iterations (untimed)
+            if world > 1:
+                dist.barrier()
+            s.record()
+            stats.append(step_resident())
+            e.record()
+        torch.cuda.synchronize()
+        t_wall = time.perf_counter() - t_wall0
+        clk = clocks.stop()
+        barrier()
     dev_ms = sum(s.elapsed_time(e) for s, e in ev)
     samples = sum(int(st.samples) for st in stats)
     tests = sum(int(st.sphere_tests) for st in stats)
@@ -222,6 +234,18 @@ def run_ours(args, rank: int, world: int, local_rank: int):
         trace_ms_max = trace_ms
     value = samples / (dev_ms * 1e-3) / 1e6
 
+    # ---- correctness of the N-GPU frame, outside every timed region: rank 0 renders the whole frame alone ------
+    check = {}
+    if rank == 0:
+        import hashlib
+        img = last["img"].cpu().numpy()
+        check["image_sha256"] = hashlib.sha256(img.tobytes()).hexdigest()
+        if world > 1:
+            whole, wst = r.render(cam)
+            check["image_equals_1gpu"] = bool(torch.equal(last["img"], whole))
+            check["segments_equal_1gpu"] = bool(int(wst.segments) * len(stats) == segments)
+            assert check["image_equals_1gpu"], "the N-GPU image differs from the single-GPU image"
+
     # ---- e2e: host buffers in, host buffers out, copies inside the timed region -----------------
     sph_bytes = n * C.sizeof(B.rtz_sphere)
     if world == 1:
@@ -233,9 +257,33 @@ def run_ours(args, rank: int, world: int, local_rank: int):
         torch.cuda.synchronize()
         e2e_s = time.perf_counter() - t0
         e2e_samples = W * H * spp * args.steps
-        h2d = 4 * ((n + 7) // 8 * 8) * 16 + n * 32
+        h2d = 5 * ((n + 7) // 8 * 8) * 16 + n * 32
         d2h = W * H * 3 + 64
+        e2e_api = "rtz_render (C ABI, host buffers)"
+        e2e_torchrun = None
     else:
+        # (a) the C ABI from ONE process: rank 0 drives all N GPUs through rtz_render_multi, the others keep off the GPUs
+        e2e_api = "rtz_render_multi (C ABI, host buffers; rank 0 alone drives all N GPUs, NVLink peer-store gather)"
+        if rank == 0:
+            rgb_m, st_m = pkg.render_host_multi(cam, spheres, n, num_gpus=world)   # creates the devices' contexts
+            check["cabi_image_equals_1gpu"] = bool((torch.from_numpy(rgb_m).to(dev) == whole).all().item())
+            assert check["cabi_image_equals_1gpu"], "rtz_render_multi differs from the single-GPU image"
+            check["cabi_gather"] = {1: "p2p (fused resolve + peer store)", 2: "nccl (grouped send/recv)"}.get(int(st_m.gather), "none")
+        dist.barrier(group=cpu_group)
+        e2e_s = 0.0
+        if rank == 0:
+            t0 = time.perf_counter()
+            for _ in range(args.steps):
+                rgb_m, st_m = pkg.render_host_multi(cam, spheres, n, num_gpus=world)
+            e2e_s = time.perf_counter() - t0
+        dist.barrier(group=cpu_group)
+        e2e_samples = W * H * spp * args.steps
+        h2d = world * (5 * ((n + 7) // 8 * 8) * 16 + n * 32)
+        d2h = W * H * 3 + world * 64
+        t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = t.item()
+        # (b) one process per GPU: upload + sharded render + NCCL gather + D2H on rank 0
         host_img = torch.empty((H, W, 3), dtype=torch.uint8).pin_memory() if rank == 0 else None
         barrier()
         t0 = time.perf_counter()
@@ -246,13 +294,9 @@ def run_ours(args, rank: int, world: int, local_rank: int):
                 host_img.copy_(img, non_blocking=False)           # D2H of the step's result
             dist.barrier()
         torch.cuda.synchronize()
-        e2e_s = time.perf_counter() - t0
-        t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+        t = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_s = t.item()
-        e2e_samples = W * H * spp * args.steps
-        h2d = world * (4 * ((n + 7) // 8 * 8) * 16 + n * 32)
-        d2h = W * H * 3 + world * 64
+        e2e_torchrun = e2e_samples / t.item() / 1e6
     e2e_value = e2e_samples / e2e_s / 1e6
 
     if rank != 0:
@@ -307,16 +351,20 @@ def run_ours(args, rank: int, world: int, local_rank: int):
         "config": {"workload": desc if not args.spp else desc + f" [spp overridden to {spp}]", "image": [W, H], "spp": spp,
                    "spheres": n, "depth": 50, "seed": hex(SEED), "l2": "flushed between timed steps (256 MiB write)",
                    "sharding": f"interleaved {TILE[0]}x{TILE[1]} tiles, NCCL gather to rank 0" if world > 1 else "none",
-                   "timing": "CUDA events on the launching stream per step, summed; max over ranks"},
+                   "timing": "CUDA events on the launching stream (Renderer.stream) per step, summed; max over ranks"},
         "mray_sphere_tests_per_s": round(tests / (dev_ms * 1e-3) / 1e6, 1),
         "segments_per_sample": round(segments / samples, 4),
         "wall_s_timed_region": round(t_wall, 3),
         "clocks": clk,
         "e2e": {"value": round(e2e_value, 2), "unit": "Msamples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "api": "rtz_render (C ABI, host buffers)" if world == 1 else "Renderer.upload + render_sharded + D2H"},
+                "api": e2e_api},
         "gpu_launches": int(sum(int(st.kernel_launches) for st in stats) * world + (args.steps if world > 1 else 0)),
         "roofline": roofline,
     }
+    line.update(check)
+    if e2e_torchrun is not None:
+        line["e2e_torchrun"] = {"value": round(e2e_torchrun, 2), "unit": "Msamples/s",
+                                "api": "Renderer.upload + render_sharded (torch.distributed NCCL gather) + D2H, one process per GPU"}
     if cpu:
         line["cpu_baseline"] = cpu
     if world == 1:

@@ -132,7 +132,7 @@ typedef struct rtz_stats {
                                /* src/vec.zig:126-128 unit of a zero vector); they add 0 to the    */
                                /* pixel instead of poisoning it, and are COUNTED here, not hidden  */
     uint32_t gpus;             /* devices that rendered this frame (1 unless rtz_multi_*)          */
-    uint32_t reserved;
+    uint32_t gather;           /* RTZ_GATHER_P2P / RTZ_GATHER_NCCL when gpus > 1, else 0           */
     double gather_ms;          /* multi-GPU: end of the slowest trace kernel -> whole image on     */
                                /* device 0 (tile exchange over NVLink + de-interleave)             */
 } rtz_stats;

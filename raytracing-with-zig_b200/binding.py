@@ -40,7 +40,7 @@ class rtz_stats(C.Structure):
     _fields_ = [("samples", C.c_uint64), ("segments", C.c_uint64), ("sphere_tests", C.c_uint64),
                 ("depth_capped", C.c_uint64), ("absorbed", C.c_uint64), ("kernel_launches", C.c_uint64),
                 ("trace_ms", C.c_double), ("resolve_ms", C.c_double), ("total_ms", C.c_double),
-                ("seed_used", C.c_uint64), ("nan_samples", C.c_uint64), ("gpus", C.c_uint32), ("reserved", C.c_uint32),
+                ("seed_used", C.c_uint64), ("nan_samples", C.c_uint64), ("gpus", C.c_uint32), ("gather", C.c_uint32),
                 ("gather_ms", C.c_double)]
 
 

@@ -189,7 +189,7 @@ void pick_chunks(const rtz_context* ctx, rtz::TraceParams& P, uint64_t n_local_p
     P.chunks_per_pixel = (spp + P.chunk - 1) / P.chunk;
     const uint64_t resident_warps = (uint64_t)ctx->sm_count * 24;
     uint64_t tail_pixels = (resident_warps * P.chunk * per_warp + spp - 1) / spp;
-    tail_pixels = std::min<uint64_t>(tail_pixels, n_local_pixels);
+    tail_pixels = std::min<uint64_t>(tail_pixels, per_warp > 64 ? n_local_pixels : n_local_pixels / 16);  // incoherent warps are ~10 % slower
     if (!tail || width == 0) tail_pixels = 0;
     P.tail_width = width ? width : 1;
     P.tail_blocks = (uint32_t)((tail_pixels + P.tail_width - 1) / P.tail_width);
@@ -1095,6 +1095,7 @@ int32_t rtz_multi_render(rtz_multi* m, const rtz_camera* cam, uint8_t* rgb_out, 
         total.gather_ms = std::max(0.0, total.total_ms - total.trace_ms);
         total.kernel_launches += nccl ? 1 : 0;
         total.gpus = (uint32_t)world;
+        total.gather = (uint32_t)m->gather;
         total.seed_used = seed;
         *st = total;
     }

@@ -522,6 +522,8 @@ struct Config {
     size_t samplesPerPixel = 500;
     std::string fileName = "chapter14.ppm";
     std::optional<uint64_t> seed;
+    int32_t numGpus = 1;   // NEW build option -DnumGpus=N (0 = every GPU of the box): Camera.render then goes through
+                           // rtz_render_multi — one process, no launcher (SURVEY 8b `num_gpus`, 8e)
 };
 inline Config& config() {
     static Config c;
@@ -607,7 +609,10 @@ struct Camera {
         const rtz_camera c = flat();
         const std::vector<rtz_sphere> spheres = scene.world.flat();
         std::vector<uint8_t> rgb(3 * image.width * image.height);
-        check(rtz_render(&c, spheres.data(), spheres.size(), rgb.data(), stats));
+        if (config().numGpus == 1)
+            check(rtz_render(&c, spheres.data(), spheres.size(), rgb.data(), stats));
+        else
+            check(rtz_render_multi(&c, spheres.data(), spheres.size(), config().numGpus, rgb.data(), stats));
         check(rtz_write_ppm(("images/" + config().fileName).c_str(), image.width, image.height, rgb.data()));
     }
 };

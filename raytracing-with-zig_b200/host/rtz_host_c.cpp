@@ -58,7 +58,8 @@ int32_t rtzh_camera_build(uint64_t width, double aspect, const double look_from[
 
 // main(): config -> Scene -> Camera -> render -> images/<fileName>.  Returns the rtz status.
 int32_t rtzh_main(uint64_t img_width, uint64_t samples_per_pixel, const char* file_name, uint64_t seed,
-                  int32_t has_seed, rtz_stats* stats) {
+                  int32_t has_seed, int32_t num_gpus, rtz_stats* stats) {
+    config().numGpus = num_gpus;
     config().imgWidth = img_width;
     config().samplesPerPixel = samples_per_pixel;
     config().fileName = file_name ? file_name : "chapter14.ppm";
@@ -93,6 +94,49 @@ int32_t rtzh_list_hit(const rtz_sphere* sp, uint64_t n, const double o[3], const
             out->point[0] = r->point.x, out->point[1] = r->point.y, out->point[2] = r->point.z;
             out->normal[0] = r->normal.x, out->normal[1] = r->normal.y, out->normal[2] = r->normal.z;
         }
+        return RTZ_OK;
+    } catch (const RenderFailed& e) {
+        return e.status;
+    }
+}
+
+// PPM.init + PPM.save (ASCII P3, src/ppm.zig:25-39) / PPM.saveBinary (:42-60) for a caller-filled pixel array
+// (3 f64 per pixel, or NULL for the all-zero image PPM.init leaves behind); Color.toRgb runs on the device.
+int32_t rtzh_ppm_save(const char* path, uint64_t width, uint64_t height, const double* pixels, int32_t binary) {
+    try {
+        PPM ppm = PPM::init(width, height);
+        if (pixels)
+            for (size_t i = 0; i < ppm.pixels.size(); ++i) ppm.pixels[i] = Color::init(pixels[3 * i], pixels[3 * i + 1], pixels[3 * i + 2]);
+        if (binary) ppm.saveBinary(path);
+        else ppm.save(path);
+        ppm.deinit();
+        return RTZ_OK;
+    } catch (const RenderFailed& e) {
+        return e.status;
+    }
+}
+
+// Color.fromValue / toValue / fromRgb / toRgb (src/color.zig:30-80)
+void rtzh_color_from_value(uint32_t value, double out[3]) {
+    const Color c = Color::fromValue(value);
+    out[0] = c.pixel.x, out[1] = c.pixel.y, out[2] = c.pixel.z;
+}
+void rtzh_color_from_rgb(uint8_t r, uint8_t g, uint8_t b, double out[3]) {
+    const Color c = Color::fromRgb(RGB{r, g, b});
+    out[0] = c.pixel.x, out[1] = c.pixel.y, out[2] = c.pixel.z;
+}
+int32_t rtzh_color_to_value(const double in[3], uint32_t* out) {
+    try {
+        *out = Color::init(in[0], in[1], in[2]).toValue();
+        return RTZ_OK;
+    } catch (const RenderFailed& e) {
+        return e.status;
+    }
+}
+int32_t rtzh_color_to_rgb(const double in[3], uint8_t out[3]) {
+    try {
+        const RGB c = Color::init(in[0], in[1], in[2]).toRgb();
+        out[0] = c.r, out[1] = c.g, out[2] = c.b;
         return RTZ_OK;
     } catch (const RenderFailed& e) {
         return e.status;

@@ -30,7 +30,17 @@ def hostlib() -> C.CDLL:
         l.rtzh_camera_build.argtypes = [u64, f64, B.D3, B.D3, B.D3, f64, f64, f64, u64, u64, u64, i32,
                                         C.POINTER(B.rtz_camera)]
         l.rtzh_main.restype = i32
-        l.rtzh_main.argtypes = [u64, u64, C.c_char_p, u64, i32, C.POINTER(B.rtz_stats)]
+        l.rtzh_main.argtypes = [u64, u64, C.c_char_p, u64, i32, i32, C.POINTER(B.rtz_stats)]
+        l.rtzh_ppm_save.restype = i32
+        l.rtzh_ppm_save.argtypes = [C.c_char_p, u64, u64, C.POINTER(f64), i32]
+        l.rtzh_color_from_value.restype = None
+        l.rtzh_color_from_value.argtypes = [C.c_uint32, B.D3]
+        l.rtzh_color_from_rgb.restype = None
+        l.rtzh_color_from_rgb.argtypes = [C.c_uint8, C.c_uint8, C.c_uint8, B.D3]
+        l.rtzh_color_to_value.restype = i32
+        l.rtzh_color_to_value.argtypes = [B.D3, C.POINTER(C.c_uint32)]
+        l.rtzh_color_to_rgb.restype = i32
+        l.rtzh_color_to_rgb.argtypes = [B.D3, C.c_uint8 * 3]
         l.rtzh_list_hit.restype = i32
         l.rtzh_list_hit.argtypes = [C.POINTER(B.rtz_sphere), u64, B.D3, B.D3, f64, f64, C.POINTER(B.rtz_hit)]
         _lib = l
@@ -74,8 +84,43 @@ def main_camera(width: int, spp: int, seed=None) -> B.rtz_camera:
     return camera_build(width, 16.0 / 9.0, (13, 2, 3), (0, 0, 0), 20, focus_dist=10.0, defocus_angle=0.6, spp=spp, seed=seed)
 
 
-def run_main(img_width: int, spp: int, file_name: str, seed=None):
-    """main(): renders to images/<file_name> under the current directory.  Returns rtz_stats."""
+def run_main(img_width: int, spp: int, file_name: str, seed=None, num_gpus: int = 1):
+    """main(): renders to images/<file_name> under the current directory (-DnumGpus=N: on N GPUs of the box,
+    0 = all, from this one process).  Returns rtz_stats."""
     st = B.rtz_stats()
-    B.check(hostlib().rtzh_main(img_width, spp, file_name.encode(), seed or 0, 0 if seed is None else 1, C.byref(st)))
+    B.check(hostlib().rtzh_main(img_width, spp, file_name.encode(), seed or 0, 0 if seed is None else 1, int(num_gpus),
+                                C.byref(st)))
     return st
+
+
+def ppm_save(path: str, width: int, height: int, pixels=None, binary: bool = False) -> None:
+    """PPM.init(width, height) [+ caller-filled pixels, 3 f64 each] then PPM.save (P3) / PPM.saveBinary (P6)."""
+    arr = None
+    if pixels is not None:
+        flat = [float(v) for px in pixels for v in px]
+        arr = (C.c_double * len(flat))(*flat)
+    B.check(hostlib().rtzh_ppm_save(str(path).encode(), width, height, arr, 1 if binary else 0))
+
+
+def color_from_value(value: int):
+    out = B.D3()
+    hostlib().rtzh_color_from_value(value, out)
+    return tuple(out)
+
+
+def color_from_rgb(r: int, g: int, b: int):
+    out = B.D3()
+    hostlib().rtzh_color_from_rgb(r, g, b, out)
+    return tuple(out)
+
+
+def color_to_value(rgb) -> int:
+    out = C.c_uint32()
+    B.check(hostlib().rtzh_color_to_value(B.D3(*[float(x) for x in rgb]), C.byref(out)))
+    return int(out.value)
+
+
+def color_to_rgb(rgb):
+    out = (C.c_uint8 * 3)()
+    B.check(hostlib().rtzh_color_to_rgb(B.D3(*[float(x) for x in rgb]), out))
+    return tuple(out)

@@ -9,6 +9,7 @@
 const std = @import("std");
 
 // ---- include/rtz.h, as extern structs (fixed-width ints and f64 only) -------------------------
+pub const RTZ_ABI_VERSION: i32 = 2;
 pub const RTZ_OK: i32 = 0;
 pub const RTZ_MODE_PATH: i32 = 0;
 
@@ -53,9 +54,63 @@ pub const rtz_stats = extern struct {
     resolve_ms: f64,
     total_ms: f64,
     seed_used: u64,
+    nan_samples: u64,
+    gpus: u32,
+    gather: u32,
+    gather_ms: f64,
 };
 
+// Layout contract with include/rtz.h, checked by the Zig compiler when this file is built AND by this
+// repository's CI without a Zig compiler: tests/test_abi_symbols.py parses the numbers below and compares them
+// with sizeof / offsetof from a C compiler on rtz.h, and the field lists above with the header's.
+comptime {
+    std.debug.assert(@sizeOf(rtz_sphere) == 80);
+    std.debug.assert(@offsetOf(rtz_sphere, "center") == 0);
+    std.debug.assert(@offsetOf(rtz_sphere, "radius") == 24);
+    std.debug.assert(@offsetOf(rtz_sphere, "mat_type") == 32);
+    std.debug.assert(@offsetOf(rtz_sphere, "reserved") == 36);
+    std.debug.assert(@offsetOf(rtz_sphere, "albedo") == 40);
+    std.debug.assert(@offsetOf(rtz_sphere, "fuzz") == 64);
+    std.debug.assert(@offsetOf(rtz_sphere, "refraction_index") == 72);
+    std.debug.assert(@sizeOf(rtz_camera) == 224);
+    std.debug.assert(@offsetOf(rtz_camera, "width") == 0);
+    std.debug.assert(@offsetOf(rtz_camera, "height") == 8);
+    std.debug.assert(@offsetOf(rtz_camera, "center") == 16);
+    std.debug.assert(@offsetOf(rtz_camera, "pixel0") == 40);
+    std.debug.assert(@offsetOf(rtz_camera, "du") == 64);
+    std.debug.assert(@offsetOf(rtz_camera, "dv") == 88);
+    std.debug.assert(@offsetOf(rtz_camera, "defocus_disk_u") == 112);
+    std.debug.assert(@offsetOf(rtz_camera, "defocus_disk_v") == 136);
+    std.debug.assert(@offsetOf(rtz_camera, "defocus_angle") == 160);
+    std.debug.assert(@offsetOf(rtz_camera, "samples_per_pixel") == 168);
+    std.debug.assert(@offsetOf(rtz_camera, "bounce_max") == 176);
+    std.debug.assert(@offsetOf(rtz_camera, "pixel_samples_scale") == 184);
+    std.debug.assert(@offsetOf(rtz_camera, "t_min") == 192);
+    std.debug.assert(@offsetOf(rtz_camera, "t_max") == 200);
+    std.debug.assert(@offsetOf(rtz_camera, "seed") == 208);
+    std.debug.assert(@offsetOf(rtz_camera, "has_seed") == 216);
+    std.debug.assert(@offsetOf(rtz_camera, "mode") == 220);
+    std.debug.assert(@sizeOf(rtz_stats) == 104);
+    std.debug.assert(@offsetOf(rtz_stats, "samples") == 0);
+    std.debug.assert(@offsetOf(rtz_stats, "segments") == 8);
+    std.debug.assert(@offsetOf(rtz_stats, "sphere_tests") == 16);
+    std.debug.assert(@offsetOf(rtz_stats, "depth_capped") == 24);
+    std.debug.assert(@offsetOf(rtz_stats, "absorbed") == 32);
+    std.debug.assert(@offsetOf(rtz_stats, "kernel_launches") == 40);
+    std.debug.assert(@offsetOf(rtz_stats, "trace_ms") == 48);
+    std.debug.assert(@offsetOf(rtz_stats, "resolve_ms") == 56);
+    std.debug.assert(@offsetOf(rtz_stats, "total_ms") == 64);
+    std.debug.assert(@offsetOf(rtz_stats, "seed_used") == 72);
+    std.debug.assert(@offsetOf(rtz_stats, "nan_samples") == 80);
+    std.debug.assert(@offsetOf(rtz_stats, "gpus") == 88);
+    std.debug.assert(@offsetOf(rtz_stats, "gather") == 92);
+    std.debug.assert(@offsetOf(rtz_stats, "gather_ms") == 96);
+}
+
 pub extern "rtz" fn rtz_render(camera: *const rtz_camera, spheres: [*]const rtz_sphere, n_spheres: u64, rgb_out: [*]u8, stats_out: ?*rtz_stats) i32;
+/// The same call on `num_gpus` GPUs of the box (<= 0: all of them) driven by THIS process: no launcher, no MPI.
+pub extern "rtz" fn rtz_render_multi(camera: *const rtz_camera, spheres: [*]const rtz_sphere, n_spheres: u64, num_gpus: i32, rgb_out: [*]u8, stats_out: ?*rtz_stats) i32;
+pub extern "rtz" fn rtz_abi_version() i32;
 pub extern "rtz" fn rtz_write_ppm(path: [*:0]const u8, width: u64, height: u64, rgb: [*]const u8) i32;
 pub extern "rtz" fn rtz_strerror(status: i32) [*:0]const u8;
 // resident API + device-side Scene.generateWorld (kind 0 final world, 1 chapter 13, 2 sweep of n spheres)
@@ -130,14 +185,20 @@ pub fn flattenCamera(cam: anytype) rtz_camera {
 
 /// Body of `Camera.render` (camera.zig:123-145) on the B200: one C-ABI call instead of the
 /// rows x columns x samples loop nest, then the same P6 file PPM.saveBinary writes.
-pub fn render(cam: anytype, comptime path: [:0]const u8) RenderError!void {
+/// `num_gpus` comes from the new build option -DnumGpus (1 by default; 0 = every GPU of the box).
+pub fn render(cam: anytype, comptime path: [:0]const u8, num_gpus: i32) RenderError!void {
+    if (rtz_abi_version() != RTZ_ABI_VERSION) return error.RenderFailed;
     const spheres = flattenWorld(cam.alloc, cam.scene.world) catch return error.RenderFailed;
     defer cam.alloc.free(spheres);
     const c = flattenCamera(cam);
     const rgb = cam.alloc.alloc(u8, 3 * cam.image.width * cam.image.height) catch return error.RenderFailed;
     defer cam.alloc.free(rgb);
-    if (rtz_render(&c, spheres.ptr, spheres.len, rgb.ptr, null) != RTZ_OK) {
-        std.log.err("rtz_render: {s}", .{rtz_last_error()});
+    const status = if (num_gpus == 1)
+        rtz_render(&c, spheres.ptr, spheres.len, rgb.ptr, null)
+    else
+        rtz_render_multi(&c, spheres.ptr, spheres.len, num_gpus, rgb.ptr, null);
+    if (status != RTZ_OK) {
+        std.log.err("rtz_render: {s}: {s}", .{ rtz_strerror(status), rtz_last_error() });
         return error.RenderFailed;
     }
     if (rtz_write_ppm(path.ptr, c.width, c.height, rgb.ptr) != RTZ_OK) return error.RenderFailed;

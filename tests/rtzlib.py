@@ -70,7 +70,7 @@ class Stats(C.Structure):
         ("seed_used", C.c_uint64),
         ("nan_samples", C.c_uint64),
         ("gpus", C.c_uint32),
-        ("reserved", C.c_uint32),
+        ("gather", C.c_uint32),
         ("gather_ms", C.c_double),
     ]
 

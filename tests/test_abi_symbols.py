@@ -46,6 +46,73 @@ def test_struct_layouts_match_header(pkg):
                      C.sizeof(R.Scatter)]
 
 
+ZIG = R.ROOT / "raytracing-with-zig_b200" / "zig"
+
+
+def _c_struct_fields(name):
+    """[(field, ctype, array_len)] of a typedef struct in rtz.h, in declaration order."""
+    text = re.sub(r"/\*.*?\*/", "", HEADER.read_text(), flags=re.S)
+    body = re.search(r"typedef struct %s \{(.*?)\} %s;" % (name, name), text, flags=re.S).group(1)
+    out = []
+    for decl in body.split(";"):
+        decl = decl.strip()
+        if not decl:
+            continue
+        ctype, names = decl.split(None, 1)
+        for nm in names.split(","):
+            m = re.match(r"\s*(\w+)(?:\[(\d+)\])?\s*$", nm)
+            out.append((m.group(1), ctype, int(m.group(2) or 0)))
+    return out
+
+
+def test_zig_glue_matches_the_header_without_a_zig_compiler(pkg, tmp_path):
+    """the Zig host layer cannot be compiled here (no zig in the image), so it is tied to
+    include/rtz.h mechanically: (1) every extern struct in zig/rtz.zig lists the header's fields in the header's
+    order with the matching Zig type; (2) the sizes and offsets in its `comptime` assertions are the ones a C
+    compiler computes from rtz.h; (3) every `extern "rtz" fn` it declares is exported by librtz.so; (4) the three
+    patches under zig/patch/ apply to the reference tree when it is present."""
+    zig = (ZIG / "rtz.zig").read_text()
+    zig_type = {"double": "f64", "uint64_t": "u64", "int32_t": "i32", "uint32_t": "u32"}
+    asserted = {}
+    for kind, st, field, val in re.findall(r"std\.debug\.assert\(@(sizeOf|offsetOf)\((\w+)(?:, \"(\w+)\")?\) == (\d+)\);", zig):
+        asserted[(st, field)] = int(val)
+    lines = ["#include <stdio.h>", "#include <stddef.h>", '#include "rtz.h"', "int main(void){"]
+    expect_keys = []
+    for st in ("rtz_sphere", "rtz_camera", "rtz_stats"):
+        fields = _c_struct_fields(st)
+        zbody = re.search(r"pub const %s = extern struct \{(.*?)\n\};" % st, zig, flags=re.S).group(1)
+        zfields = re.findall(r"^\s*(\w+): (\[3\])?(\w+)", zbody, flags=re.M)
+        assert [(f, zig_type[t], n) for f, t, n in fields] == [(f, t, 3 if arr else 0) for f, arr, t in zfields], st
+        lines.append('printf("%%zu\\n", sizeof(%s));' % st)
+        expect_keys.append((st, ""))
+        for f, _, _ in fields:
+            lines.append('printf("%%zu\\n", offsetof(%s, %s));' % (st, f))
+            expect_keys.append((st, f))
+    lines.append("return 0;}")
+    (tmp_path / "o.c").write_text("\n".join(lines))
+    subprocess.run(["gcc", "-std=c99", "-I", str(HEADER.parent), "-o", str(tmp_path / "o"), str(tmp_path / "o.c")], check=True)
+    vals = [int(x) for x in subprocess.run([str(tmp_path / "o")], capture_output=True, text=True, check=True).stdout.split()]
+    assert dict(zip(expect_keys, vals)) == asserted          # every size / offset, nothing missing, nothing extra
+    lib = C.CDLL(str(pkg.binding.LIB_PATH))
+    externs = re.findall(r'pub extern "rtz" fn (\w+)\(', zig)
+    assert "rtz_render" in externs and "rtz_render_multi" in externs
+    assert all(hasattr(lib, fn) for fn in externs), [fn for fn in externs if not hasattr(lib, fn)]
+    assert "RTZ_ABI_VERSION: i32 = %d" % pkg.lib().rtz_abi_version() in zig
+    patches = sorted((ZIG / "patch").glob("*.patch"))
+    assert [p.name for p in patches] == ["build.zig.patch", "camera.zig.patch", "main.zig.patch"]
+    ref = Path("/root/reference")
+    if (ref / "src" / "camera.zig").exists():                 # only in the build container; the GPU box has no reference
+        import shutil
+        work = tmp_path / "ref"
+        shutil.copytree(ref / "src", work / "src")
+        shutil.copy(ref / "build.zig", work / "build.zig")
+        for p in patches:
+            r = subprocess.run(["patch", "-p1", "-i", str(p)], cwd=work, capture_output=True, text=True)
+            assert r.returncode == 0, r.stdout + r.stderr
+        cam = (work / "src" / "camera.zig").read_text()
+        assert 'rtz.render(self, "images/" ++ config.fileName, config.numGpus)' in cam and "self.rayColor(ray);\n                }\n                const avgColor" not in cam
+
+
 def test_sm100a_code_with_tma_in_the_binary(pkg):
     """The shipped kernels are sm_100a SASS and the scene staging is a TMA bulk copy (UBLKCP)."""
     out = subprocess.run(["cuobjdump", "-sass", str(pkg.binding.LIB_PATH)], capture_output=True, text=True).stdout

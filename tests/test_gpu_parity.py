@@ -229,6 +229,86 @@ def test_final_scene_rmse_vs_f64_reference(gpu, orc):
     assert st.depth_capped / st.samples <= 5e-4
 
 
+@pytest.mark.timeout(1200)
+def test_final_scene_400spp_vs_both_reference_renders(gpu, orc):
+    """north_star: "stochastic scenes must agree with the reference CPU render ... at matched high spp".  The final
+    scene at 400x225 and 400 spp (N >= 400) against BOTH CPU restatements of the reference: the f64
+    render with per-sample Philox streams (all host threads) and the render the reference really is — ONE thread,
+    ONE shared sequential Xoshiro256++ stream (about 1.5 minutes).  Tolerance, as everywhere: RMSE of the 8-bit
+    images <= 1.25 x the reference's own seed-to-seed RMSE at this spp (~2.0 levels, PSNR ~42 dB), |mean signed
+    error| <= 0.25 level per channel, segments per sample within 1 %, depth-capped samples <= 0.05 %."""
+    prng, sp, n = R.final_scene(0xDEADBEEF)
+    cam = R.main_camera(400, 400, seed=0xDEADBEEF)
+    gpu.upload(sp, n)
+    img, st = gpu.render(cam)
+    g = img.cpu().numpy().astype(np.float64)
+    assert st.nan_samples == 0
+    threads = max(1, orc.orc_hardware_threads())
+    u8 = lambda x: x.ctypes.data_as(C.POINTER(C.c_uint8))
+    a, b, x = (np.zeros((225, 400, 3), np.uint8) for _ in range(3))
+    ast, xst = R.Stats(), R.Stats()
+    assert orc.orc_render_philox64(C.byref(cam), sp, n, 1, threads, u8(a), None, C.byref(ast)) == 0
+    assert orc.orc_render_philox64(C.byref(cam), sp, n, 2, threads, u8(b), None, None) == 0
+    assert orc.orc_render_reference(C.byref(cam), sp, n, prng, u8(x), None, C.byref(xst)) == 0   # sequential Xoshiro
+    floor = _rmse(a, b)
+    assert 1.5 < floor < 2.6, floor                      # SURVEY 4.4: 41 / sqrt(400) = 2.05
+    for name, ref, rst in (("philox64", a, ast), ("xoshiro, 1 thread", x, xst)):
+        err = _rmse(g, ref)
+        bias = np.abs((g - ref.astype(np.float64)).mean(axis=(0, 1)))
+        assert err <= 1.25 * floor, (name, err, floor)
+        assert bias.max() <= 0.25, (name, bias)
+        assert abs(st.segments / st.samples - rst.segments / rst.samples) <= 0.01 * rst.segments / rst.samples, name
+    assert st.depth_capped / st.samples <= 5e-4
+
+
+def test_bad_scene_and_camera_values_are_refused(pkg, gpu):
+    """A radius-0 sphere makes the reference panic in Vec.divScalar the moment it is hit (src/vec.zig:39-45,
+    src/sphere.zig:45), NaN / infinite inputs only yield NaN samples: the library refuses them with
+    RTZ_ERR_BAD_ARG instead of rendering something, and a refused upload leaves the context's scene as it was
+    (a CUDA failure in the middle of an upload leaves an EMPTY world, never stale geometry); NaN samples, should
+    one ever occur, are counted in rtz_stats, not hidden."""
+    sp, n = R.chapter13_scene()
+    cam = R.build_camera(64, 16.0 / 9.0, (0, 0, 0), (0, 0, -1), 90, spp=2, seed=1)
+    good, gst = pkg.render_host(cam, sp, n)
+    assert gst.nan_samples == 0 and gst.gpus == 1
+
+    def with_sphere(i, **kw):
+        arr = (R.Sphere * n)()
+        for k in range(n):
+            arr[k] = sp[k]
+        for key, val in kw.items():
+            setattr(arr[i], key, val)
+        return arr
+
+    nan, inf = float("nan"), float("inf")
+    bad_scenes = [with_sphere(1, radius=0.0), with_sphere(1, radius=-1.0),      # Sphere.init clamps to 0 (src/sphere.zig:21)
+                  with_sphere(0, radius=nan), with_sphere(2, radius=inf), with_sphere(0, center=R.d3((0, nan, 0))),
+                  with_sphere(0, albedo=R.d3((1, inf, 1))), with_sphere(4, fuzz=nan), with_sphere(2, refraction_index=0.0),
+                  with_sphere(2, refraction_index=nan), with_sphere(3, mat_type=7)]
+    for arr in bad_scenes:
+        with pytest.raises(pkg.RtzError) as e:
+            pkg.render_host(cam, arr, n)
+        assert e.value.status == 1
+    gpu.upload(sp, n)
+    with pytest.raises(pkg.RtzError):
+        gpu.upload(bad_scenes[0], n)              # refused during validation, before the context is touched:
+    img, st = gpu.render(cam)                     # the scene installed before is still there, intact
+    assert np.array_equal(img.cpu().numpy(), good) and st.segments == gst.segments
+    for field, val in (("center", R.d3((nan, 0, 0))), ("pixel0", R.d3((0, inf, 0))), ("du", R.d3((nan, 0, 0))),
+                       ("defocus_angle", nan), ("pixel_samples_scale", inf), ("t_min", nan), ("t_max", nan)):
+        c2 = R.Camera.from_buffer_copy(bytes(cam))
+        setattr(c2, field, val)
+        with pytest.raises(pkg.RtzError) as e:
+            pkg.render_host(c2, sp, n)
+        assert e.value.status == 1, field
+    # sizes that overflow 32-bit pixel indices, degenerate tiles
+    c2 = pkg.rtz_camera.from_buffer_copy(bytes(cam))
+    c2.width, c2.height = 1 << 33, 1 << 33
+    tiny = np.zeros(3, np.uint8).ctypes.data_as(C.POINTER(C.c_uint8))
+    assert pkg.lib().rtz_render(C.byref(c2), C.cast(sp, C.POINTER(pkg.rtz_sphere)), n, tiny, None) == 1
+    assert pkg.lib().rtz_shard_pixels(64, 36, C.byref(pkg.rtz_shard(0, 2, 65536, 65536))) == 0
+
+
 # ------------------------------------------------------------------ sharding: any world == 1 GPU
 @pytest.mark.parametrize("world,tile", [(2, (16, 16)), (3, (32, 8)), (8, (16, 16)), (4, (7, 5))])
 def test_interleaved_tiles_equal_whole_frame(pkg, gpu, orc, world, tile):

@@ -97,3 +97,60 @@ def test_host_hittable_list_hit_runs_on_device(host):
     rc = host.hostlib().rtzh_list_hit(C.cast(four, C.POINTER(pkg.rtz_sphere)), 4, R.d3((0, 0, 0)), R.d3((0, 0, -1)), -6.0,
                                       6.0, C.byref(h))
     assert rc == 0 and h.hit == 1 and h.t == 1.0 and list(h.normal) == [0, 0, 1]
+
+
+# ------------------------------------------------------------------ P3 writer and Color converters
+def test_color_from_value_and_from_rgb_are_the_reference_formulas(host):
+    """Color.fromValue / Color.fromRgb (reference src/color.zig:30-38, 53-61): channel / 255.999 in f64.  Host-only."""
+    assert host.color_from_value((255 << 16) | (0 << 8) | 255) == (255 / 255.999, 0.0, 255 / 255.999)
+    assert host.color_from_value(0x123456) == (0x12 / 255.999, 0x34 / 255.999, 0x56 / 255.999)
+    assert host.color_from_rgb(255, 0, 255) == (255 / 255.999, 0.0, 255 / 255.999)
+    assert host.color_from_rgb(1, 2, 3) == (1 / 255.999, 2 / 255.999, 3 / 255.999)
+
+
+@pytest.mark.gpu
+def test_color_converters_kats(host):
+    """The reference's own KATs, src/color.zig:122-163 — Color.toRgb (gamma 2, clamp, trunc(256 x)) runs on the device:
+    fromValue(0xFF00FF).toRgb() == (255, 0, 255); Color(1, 0, 1).toValue() == 0xFF00FF; fromRgb(255, 0, 255).toRgb()
+    == (255, 0, 255); Color(0, .5, .75).toRgb() == (0, 181, 221)."""
+    assert host.color_to_rgb(host.color_from_value(0xFF00FF)) == (255, 0, 255)
+    assert host.color_to_value((1.0, 0.0, 1.0)) == 0xFF00FF
+    assert host.color_to_rgb(host.color_from_rgb(255, 0, 255)) == (255, 0, 255)
+    assert host.color_to_rgb((0.0, 0.5, 0.75)) == (0, 181, 221)
+    assert host.color_to_rgb((-1.0, 0.0, 4.0)) == (0, 0, 255)          # linearToGamma: -1 -> 0, 4 -> 2 -> clamp .999
+
+
+@pytest.mark.gpu
+def test_ppm_save_ascii_and_binary_kats(host, tmp_path):
+    """PPM.save (ASCII P3, src/ppm.zig:25-39) and PPM.saveBinary (:42-60) of the product's host mirror against the
+    reference's KATs: a fresh 1x1 PPM saves as "P3\\n1 1\\n255\\n0 0 0\\n" (:72-90) and as test-files/test-binary.ppm
+    (:92-106); a filled image writes one "r g b" line per pixel, row-major."""
+    p3, p6 = tmp_path / "test.ppm", tmp_path / "test-binary.ppm"
+    host.ppm_save(p3, 1, 1)
+    assert p3.read_bytes() == b"P3\n1 1\n255\n0 0 0\n"
+    host.ppm_save(p6, 1, 1, binary=True)
+    assert p6.read_bytes() == (R.GOLDEN / "test-binary.ppm").read_bytes()
+    host.ppm_save(p3, 2, 2, [(0.0, 0.5, 0.75), (1.0, 0.0, 1.0), (0.25, 0.25, 0.25), (4.0, -1.0, 0.0)])
+    assert p3.read_bytes() == b"P3\n2 2\n255\n0 181 221\n255 0 255\n128 128 128\n255 0 0\n"
+    host.ppm_save(p6, 2, 2, [(0.0, 0.5, 0.75), (1.0, 0.0, 1.0), (0.25, 0.25, 0.25), (4.0, -1.0, 0.0)], binary=True)
+    assert p6.read_bytes() == b"P6\n2 2\n255\n" + bytes([0, 181, 221, 255, 0, 255, 128, 128, 128, 255, 0, 0]) + b"\n"
+    with pytest.raises(Exception):
+        host.ppm_save(tmp_path / "nodir" / "x.ppm", 1, 1)
+
+
+@pytest.mark.gpu
+def test_main_with_num_gpus_option(host, tmp_path):
+    """-DnumGpus=0 (every GPU of the box): main() goes through rtz_render_multi from this one process and writes
+    the same file as the single-GPU run."""
+    cwd = os.getcwd()
+    os.chdir(tmp_path)
+    try:
+        os.mkdir("images")
+        st1 = host.run_main(160, 6, "one.ppm", 0xDEADBEEF)
+        stn = host.run_main(160, 6, "all.ppm", 0xDEADBEEF, num_gpus=0)
+    finally:
+        os.chdir(cwd)
+    import torch
+    assert stn.gpus == torch.cuda.device_count() and st1.gpus == 1
+    assert (tmp_path / "images" / "one.ppm").read_bytes() == (tmp_path / "images" / "all.ppm").read_bytes()
+    assert (stn.samples, stn.segments) == (st1.samples, st1.segments)
