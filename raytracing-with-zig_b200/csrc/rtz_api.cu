@@ -12,8 +12,12 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <condition_variable>
+#include <functional>
 #include <map>
 #include <mutex>
+#include <thread>
+#include <memory>
 #include <string>
 #include <vector>
 
@@ -109,10 +113,9 @@ struct rtz_context {
     int n_spheres = 0, n_pad = 0;
     // frame state
     DevBuf<unsigned long long> accum;
-    DevBuf<unsigned long long> counters;  // [0] queue head, [1..4] stats, [5] BVH tests, [6] NaN samples
-    DevBuf<uint32_t> order;               // queue order of the frame (classify_kernel) + its two cursors
+    DevBuf<unsigned long long> counters;  // [0] queue head, [1..4] stats, [5] BVH tests, [6] NaN samples, [8] drain pool {parked, next}
+    DevBuf<float4> pool;                  // drain pool: 4 float4 per parked path, 64 paths per resident warp
     uint64_t frame_launches = 0;          // kernels launched for the frame in flight
-    int n_dielectric = 0;                 // spheres of glass in the scene: without any, the queue keeps image order
     DevBuf<unsigned long long> timeline;  // RTZ_TIMELINE=1: per-warp {start, queue dry, done} stamps of the last frame
     DevBuf<uint8_t> rgb;                  // used by the host-buffer entry points
     DevBuf<double> linear;
@@ -172,32 +175,18 @@ rtz::DevCamera to_dev_camera(const rtz_camera& c, uint64_t seed) {
     return d;
 }
 
-// Work chunks (TraceParams): runs of <= 256 samples of ONE pixel, except for the last pixels of the queue, which
-// are cut ACROSS pixels (32 pixels x one sample index).  The tail region holds about four big chunks per resident
-// warp: enough small work for the early finishers while the others end their last big chunk, even an expensive
-// one.  `tail` = false: no tail region (kernels whose regeneration only knows one-pixel chunks).
-// RTZ_CHUNK / RTZ_TAIL_WIDTH (0 = no tail region) / RTZ_TAIL_CHUNKS / RTZ_COOP_MAX override (experiments; the
-// image does not depend on any of them: tested).
-void pick_chunks(const rtz_context* ctx, rtz::TraceParams& P, uint64_t n_local_pixels, bool tail) {
-    uint32_t cap = 256u, width = 32u, per_warp = 4u, coop = 16u;
+// Work chunks: runs of <= 128 samples of ONE pixel (RTZ_CHUNK overrides the cap: experiments; the image does not
+// depend on it).  A warp keeps its chunk until it is used up, so the chunk bounds how long the last warps run on
+// after the queue is dry: measured on 1/8 shards of C3, 128 beats 256 (19.79 vs 19.95 ms) and 64 (19.88 ms).  Schedules that cut the END of the queue into small or across-pixel chunks, reorder it (pixels
+// that look into glass first) or let drained warps sweep sphere-parallel were built and measured in round 2
+// (DESIGN.md §5): with the drain kernel none of them is needed, and the reordering even costs 2 %.
+void pick_chunks(rtz::TraceParams& P, uint64_t n_local_pixels) {
+    uint32_t cap = 128u;
     if (const char* e = std::getenv("RTZ_CHUNK")) cap = (uint32_t)std::max(1, std::atoi(e));
-    if (const char* e = std::getenv("RTZ_TAIL_WIDTH")) width = (uint32_t)std::min(64, std::max(0, std::atoi(e)));
-    if (const char* e = std::getenv("RTZ_TAIL_CHUNKS")) per_warp = (uint32_t)std::max(0, std::atoi(e));
-    if (const char* e = std::getenv("RTZ_COOP_MAX")) coop = (uint32_t)std::max(0, std::atoi(e));
-    const uint32_t spp = P.cam.spp;
-    P.chunk = spp < cap ? spp : cap;
-    P.chunks_per_pixel = (spp + P.chunk - 1) / P.chunk;
-    const uint64_t resident_warps = (uint64_t)ctx->sm_count * 24;
-    uint64_t tail_pixels = (resident_warps * P.chunk * per_warp + spp - 1) / spp;
-    tail_pixels = std::min<uint64_t>(tail_pixels, per_warp > 64 ? n_local_pixels : n_local_pixels / 16);  // incoherent warps are ~10 % slower
-    if (!tail || width == 0) tail_pixels = 0;
-    P.tail_width = width ? width : 1;
-    P.tail_blocks = (uint32_t)((tail_pixels + P.tail_width - 1) / P.tail_width);
-    P.tail_first_pixel = (uint32_t)(n_local_pixels - tail_pixels);
+    P.chunk = P.cam.spp < cap ? P.cam.spp : cap;
+    P.chunks_per_pixel = (P.cam.spp + P.chunk - 1) / P.chunk;
     P.n_local_pixels = (uint32_t)n_local_pixels;
-    P.n_body_chunks = (uint64_t)P.tail_first_pixel * P.chunks_per_pixel;
-    P.n_chunks = P.n_body_chunks + (uint64_t)P.tail_blocks * spp;
-    P.coop_max = coop;
+    P.n_chunks = n_local_pixels * P.chunks_per_pixel;
 }
 
 template <class Kern, class Params>
@@ -246,17 +235,25 @@ int32_t enqueue_path(rtz_context* ctx, const rtz_camera* cam, const rtz::ShardGe
     P.sh = sg;
     P.geom = ctx->geom.p, P.pairs = ctx->pairs.p, P.aux = ctx->aux.p, P.albedo = ctx->albedo.p, P.wexp = ctx->wexp.p;
     P.n_spheres = ctx->n_spheres, P.n_pad = ctx->n_pad;
-    pick_chunks(ctx, P, n_local_pixels, cam->mode == RTZ_MODE_PATH && ctx->variant != 4);
+    pick_chunks(P, n_local_pixels);
     P.accum = ctx->accum.p;
     P.counter = ctx->counters.p;
     P.stats = ctx->counters.p + 1;
     P.timeline = nullptr;
     if (const char* e = std::getenv("RTZ_TIMELINE")) {  // diagnostics: tools/tail_timeline.py reads the file back
         if (e[0] == '1') {
-            RTZ_CUDA(ctx->timeline.reserve(6 * 65536));
-            RTZ_CUDA(cudaMemsetAsync(ctx->timeline.p, 0, 6 * 65536 * sizeof(unsigned long long), ctx->stream));
+            RTZ_CUDA(ctx->timeline.reserve(4 * 65536));
+            RTZ_CUDA(cudaMemsetAsync(ctx->timeline.p, 0, 4 * 65536 * sizeof(unsigned long long), ctx->stream));
             P.timeline = ctx->timeline.p;
         }
+    }
+    // drain pool (RTZ_DRAIN=0: the warps finish their own paths in lockstep, as in round 1)
+    P.pool = nullptr, P.pool_count = reinterpret_cast<unsigned int*>(ctx->counters.p + 8);
+    const char* de = std::getenv("RTZ_DRAIN");
+    const bool drain = cam->mode == RTZ_MODE_PATH && ctx->variant != 4 && P.cam.bounce_max > 0 && !(de && de[0] == '0');
+    if (drain) {
+        RTZ_CUDA(ctx->pool.reserve(4ull * 64 * 32 * (size_t)ctx->sm_count * 2));  // 64 paths per warp, <= 64 warps per SM
+        P.pool = ctx->pool.p;
     }
     const bool use_const = ctx->n_pad <= rtz::kMaxConstSpheres && ctx->geo_const;
     const size_t smem = use_const ? 0 : (size_t)ctx->n_pad * 32;  // pair layout + per-lane rows
@@ -266,21 +263,9 @@ int32_t enqueue_path(rtz_context* ctx, const rtz_camera* cam, const rtz::ShardGe
     const bool use_global = !use_const && smem + fa.sharedSizeBytes + 1024 > ctx->smem_optin;
     RTZ_CUDA(cudaEventRecord(ctx->ev[0], ctx->stream));
     RTZ_CUDA(cudaMemsetAsync(ctx->accum.p, 0, 3 * n_local_pixels * sizeof(unsigned long long), ctx->stream));
-    RTZ_CUDA(cudaMemsetAsync(ctx->counters.p, 0, 8 * sizeof(unsigned long long), ctx->stream));
+    RTZ_CUDA(cudaMemsetAsync(ctx->counters.p, 0, 16 * sizeof(unsigned long long), ctx->stream));
     RTZ_CUDA(cudaEventRecord(ctx->ev[1], ctx->stream));
-    // queue order: pixels that look into glass first (RTZ_ORDER=0: image order)
-    P.order = nullptr;
     ctx->frame_launches = P.cam.bounce_max == 0 ? 1 : 2;
-    const char* oe = std::getenv("RTZ_ORDER");
-    if (ctx->n_dielectric > 0 && P.cam.bounce_max > 1 && n_local_pixels > 1 && !(oe && oe[0] == '0')) {
-        RTZ_CUDA(ctx->order.reserve(n_local_pixels + 2));
-        unsigned int* cursors = ctx->order.p + n_local_pixels;
-        RTZ_CUDA(cudaMemsetAsync(cursors, 0, 2 * sizeof(unsigned int), ctx->stream));
-        rtz::classify_kernel<<<(unsigned)((n_local_pixels + 127) / 128), 128, 0, ctx->stream>>>(P, ctx->order.p, cursors);
-        RTZ_CUDA(cudaGetLastError());
-        P.order = ctx->order.p;
-        ctx->frame_launches = 3;
-    }
     int32_t rc = RTZ_OK;
     if (P.cam.bounce_max == 0) {
         // `while (bounces < bounceMax)` never runs (src/camera.zig:153): every sample is black and no
@@ -326,6 +311,15 @@ int32_t enqueue_path(rtz_context* ctx, const rtz_camera* cam, const rtz::ShardGe
         }
     }
     if (rc != RTZ_OK) return rc;
+    if (drain) {  // finish what the trace kernel parked: persistent grid, one warp (or, below 64 spheres, one thread) per path
+        const unsigned blocks = (unsigned)ctx->sm_count * 8;
+        if (ctx->n_spheres >= 64)
+            rtz::drain_kernel<true><<<blocks, 128, 0, ctx->stream>>>(P);
+        else
+            rtz::drain_kernel<false><<<blocks, 128, 0, ctx->stream>>>(P);
+        RTZ_CUDA(cudaGetLastError());
+        ctx->frame_launches += 1;
+    }
     RTZ_CUDA(cudaEventRecord(ctx->ev[2], ctx->stream));
     const uint64_t n3 = 3 * n_local_pixels;
     if (out.image)
@@ -346,7 +340,7 @@ int32_t collect_path(rtz_context* ctx, const rtz_camera* cam, const rtz::ShardGe
     RTZ_CUDA(cudaStreamSynchronize(ctx->stream));
     if (const char* path = std::getenv("RTZ_TIMELINE_OUT")) {
         if (ctx->timeline.p && std::getenv("RTZ_TIMELINE") && std::getenv("RTZ_TIMELINE")[0] == '1') {
-            std::vector<unsigned long long> h(6 * 65536);
+            std::vector<unsigned long long> h(4 * 65536);
             RTZ_CUDA(cudaMemcpy(h.data(), ctx->timeline.p, h.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
             if (FILE* f = std::fopen(path, "wb")) {
                 std::fwrite(h.data(), sizeof(unsigned long long), h.size(), f);
@@ -491,7 +485,7 @@ int32_t rtz_context_create(int32_t device, void* stream, rtz_context** out) {
     }
     for (auto& e : c->ev) cudaEventCreate(&e);
     cudaMallocHost(&c->h_counters, 8 * sizeof(unsigned long long));
-    if (c->counters.reserve(8) != cudaSuccess || !c->h_counters) {
+    if (c->counters.reserve(16) != cudaSuccess || !c->h_counters) {
         rtz_context_destroy(c);
         g_last_error = "allocation failed";
         return RTZ_ERR_CUDA;
@@ -506,7 +500,7 @@ int32_t rtz_context_destroy(rtz_context* c) {
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
     c->geom.release(), c->pairs.release(), c->aux.release(), c->albedo.release(), c->dspheres.release();
-    c->accum.release(), c->counters.release(), c->rgb.release(), c->linear.release(), c->timeline.release(), c->order.release();
+    c->accum.release(), c->counters.release(), c->rgb.release(), c->linear.release(), c->timeline.release(), c->pool.release();
     c->bvh_nodes.release(), c->bvh_order.release(), c->wexp.release();
     for (auto& e : c->ev)
         if (e) cudaEventDestroy(e);
@@ -645,8 +639,6 @@ int32_t rtz_scene_upload(rtz_context* c, const rtz_sphere* sp, uint64_t n) {
     g.resize(n), w.resize(n);
     c->h_geom.swap(g), c->h_w.swap(w);  // what the BVH extension is built from, if it is ever asked for
     c->n_spheres = (int)n, c->n_pad = n_pad;
-    c->n_dielectric = 0;
-    for (uint64_t i = 0; i < n; ++i) c->n_dielectric += sp[i].mat_type == RTZ_MAT_DIELECTRIC;
     return RTZ_OK;
 }
 
@@ -871,7 +863,54 @@ NcclApi g_nccl;
 
 }  // namespace
 
+// One host thread per extra device: uploads and launches for the N devices of an rtz_multi are issued concurrently
+// (one thread walking eight devices costs ~0.1 ms per device per frame, 4 % of a 21 ms frame).  The caller's thread
+// serves device 0 itself; the ABI stays synchronous and single-entry.
+struct MultiWorker {
+    std::thread th;
+    std::mutex mu;
+    std::condition_variable cv;
+    std::function<int32_t()> job;
+    bool has_job = false, done = true, quit = false;
+    int32_t rc = RTZ_OK;
+    std::string err;
+    void loop() {
+        std::unique_lock<std::mutex> lk(mu);
+        for (;;) {
+            cv.wait(lk, [&] { return has_job || quit; });
+            if (quit) return;
+            has_job = false;
+            lk.unlock();
+            g_last_error.clear();
+            const int32_t r = job();
+            lk.lock();
+            rc = r, err = g_last_error, done = true;
+            cv.notify_all();
+        }
+    }
+    void post(std::function<int32_t()> f) {
+        std::lock_guard<std::mutex> lk(mu);
+        job = std::move(f), has_job = true, done = false;
+        cv.notify_all();
+    }
+    int32_t wait() {
+        std::unique_lock<std::mutex> lk(mu);
+        cv.wait(lk, [&] { return done; });
+        if (rc != RTZ_OK) g_last_error = err;
+        return rc;
+    }
+    void stop() {
+        {
+            std::lock_guard<std::mutex> lk(mu);
+            quit = true;
+            cv.notify_all();
+        }
+        if (th.joinable()) th.join();
+    }
+};
+
 struct rtz_multi {
+    std::vector<std::unique_ptr<MultiWorker>> workers;  // [r] for r >= 1
     std::vector<int> dev;
     std::vector<rtz_context*> ctx;
     std::vector<cudaEvent_t> done;        // per device: its resolve has finished
@@ -885,11 +924,27 @@ struct rtz_multi {
     cudaEvent_t ev_start = nullptr, ev_traced = nullptr, ev_end = nullptr;  // device 0's stream
 };
 
+namespace {
+// fn(r) for every device of the group, concurrently; the first failure is reported
+int32_t on_every_device(rtz_multi* m, const std::function<int32_t(int)>& fn) {
+    const int world = (int)m->ctx.size();
+    for (int r = 1; r < world; ++r) m->workers[r]->post([&fn, r] { return fn(r); });
+    int32_t rc = fn(0);
+    for (int r = 1; r < world; ++r) {
+        const int32_t w = m->workers[r]->wait();
+        if (rc == RTZ_OK) rc = w;
+    }
+    return rc;
+}
+}  // namespace
+
 extern "C" {
 
 int32_t rtz_multi_destroy(rtz_multi* m) {
     if (!m) return RTZ_ERR_BAD_ARG;
     DeviceGuard guard;
+    for (auto& w : m->workers)
+        if (w) w->stop();
     for (size_t r = 0; r < m->ctx.size(); ++r) {
         if (!m->ctx[r]) continue;
         cudaSetDevice(m->dev[r]);
@@ -939,6 +994,12 @@ int32_t rtz_multi_create(int32_t num_gpus, const int32_t* devices, uint32_t tile
         }
         cudaSetDevice(m->dev[r]);
         cudaEventCreateWithFlags(&m->done[r], cudaEventDisableTiming);
+    }
+    m->workers.resize(num_gpus);
+    for (int r = 1; r < num_gpus; ++r) {
+        m->workers[r] = std::make_unique<MultiWorker>();
+        MultiWorker* w = m->workers[r].get();
+        w->th = std::thread([w] { w->loop(); });
     }
     cudaSetDevice(m->dev[0]);
     cudaEventCreate(&m->ev_start), cudaEventCreate(&m->ev_traced), cudaEventCreate(&m->ev_end);
@@ -991,11 +1052,7 @@ int32_t rtz_multi_gather(const rtz_multi* m) { return m ? m->gather : -1; }
 
 int32_t rtz_multi_scene_upload(rtz_multi* m, const rtz_sphere* sp, uint64_t n) {
     if (!m) return RTZ_ERR_BAD_ARG;
-    for (rtz_context* c : m->ctx) {
-        const int32_t rc = rtz_scene_upload(c, sp, n);
-        if (rc != RTZ_OK) return rc;
-    }
-    return RTZ_OK;
+    return on_every_device(m, [&](int r) { return rtz_scene_upload(m->ctx[r], sp, n); });
 }
 
 int32_t rtz_multi_render(rtz_multi* m, const rtz_camera* cam, uint8_t* rgb_out, uint8_t** d_rgb_out, rtz_stats* st) {
@@ -1043,18 +1100,20 @@ int32_t rtz_multi_render(rtz_multi* m, const rtz_camera* cam, uint8_t* rgb_out, 
         RTZ_CUDA(cudaSetDevice(m->dev[0]));
     }
     RTZ_CUDA(cudaEventRecord(m->ev_start, c0->stream));
-    // every device's frame is enqueued before the first wait
-    for (int r = 0; r < world; ++r) {
+    // every device's frame is enqueued (by its own host thread) before the first wait
+    rc = on_every_device(m, [&](int r) -> int32_t {
         RTZ_CUDA(cudaSetDevice(m->dev[r]));
         FrameTarget out;
         if (nccl)
             out.d_rgb = r == 0 ? m->gathered.p : m->local[r];
         else
             out.image = m->image.p;  // peer memory for r >= 1
-        rc = enqueue_path(m->ctx[r], cam, sg[r], out, seed);
-        if (rc != RTZ_OK) return rc;
+        const int32_t e = enqueue_path(m->ctx[r], cam, sg[r], out, seed);
+        if (e != RTZ_OK) return e;
         RTZ_CUDA(cudaEventRecord(m->done[r], m->ctx[r]->stream));
-    }
+        return RTZ_OK;
+    });
+    if (rc != RTZ_OK) return rc;
     RTZ_CUDA(cudaSetDevice(m->dev[0]));
     RTZ_CUDA(cudaEventRecord(m->ev_traced, c0->stream));
     if (nccl) {

@@ -152,12 +152,12 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks) trace_kernel_bvh(const __g
                     exhausted = true;
                     break;
                 }
-                Chunk c;  // this kernel is launched without a tail region: every chunk is a run of one pixel
-                decode_chunk(P, cid, cam.spp, c);
-                ch_lp = queue_pixel(P, c.q0);
+                ch_lp = (uint32_t)(cid / P.chunks_per_pixel);
+                const uint32_t part = (uint32_t)(cid - (unsigned long long)ch_lp * P.chunks_per_pixel);
                 const bool inside = local_to_global(P.sh, cam.width, cam.height, ch_lp, ch_x, ch_y);
                 if (__any_sync(0xFFFFFFFFu, !inside)) continue;  // tile padding
-                ch_next = c.next, ch_end = c.end;
+                ch_next = part * P.chunk;
+                ch_end = min(ch_next + P.chunk, cam.spp);
             }
             const uint32_t avail = ch_end - ch_next;
             const uint32_t rank = __popc(need & lt_mask);

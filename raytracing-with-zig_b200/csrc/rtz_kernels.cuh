@@ -27,29 +27,21 @@ struct TraceParams {
     const float* wexp;      // [n_pad] w of the pair layout as a plain row (per-lane lookups: coop_hit, the BVH extension)
     int n_spheres;
     int n_pad;              // n rounded up to a multiple of 8 (padding spheres can never be hit)
-    // Work chunks, handed out by the global queue in index order.  The frame's first `tail_first_pixel` local
-    // pixels are cut into runs of `chunk` samples of ONE pixel (a warp's 64 paths then share their camera
-    // geometry).  The remaining pixels — the END of the queue — are cut the other way: a chunk is ONE sample
-    // index of `tail_width` consecutive pixels.  Small chunks make all warps run dry within a few microseconds
-    // of each other, and cutting across pixels spreads the samples of an expensive pixel (paths trapped inside
-    // a glass sphere: 4x the bounces, measured with RTZ_TIMELINE) over many warps instead of leaving one warp
-    // with 64 deep paths after everybody else has finished.
-    uint32_t chunk;         // samples per work chunk (body of the queue)
+    // Work chunks = runs of `chunk` samples of ONE pixel (a warp's 64 paths then share their camera geometry: warps
+    // fed with samples of different pixels measured 7-16 % slower), handed out by the global queue in index order.
+    uint32_t chunk;         // samples per work chunk
     uint32_t chunks_per_pixel;
-    uint32_t tail_width;    // pixels per chunk at the end of the queue
-    uint32_t tail_blocks;   // chunks per sample index there: ceil(tail pixels / tail_width)
-    uint32_t tail_first_pixel;  // first local pixel of the tail region
     uint32_t n_local_pixels;
-    const uint32_t* order;  // queue position q -> local pixel, or null for the identity.  Written by classify_kernel:
-                            // pixels whose centre ray enters glass come FIRST (their paths are 4x as long: longest
-                            // processing time first, so that no warp is left with an expensive pixel at the end)
-    uint32_t coop_max;      // queue drained and at most this many live paths in the warp: sphere-parallel sweep
-    uint64_t n_body_chunks; // tail_first_pixel * chunks_per_pixel
-    uint64_t n_chunks;      // n_body_chunks + tail_blocks * spp
+    uint64_t n_chunks;      // n_local_pixels(padded) * chunks_per_pixel
     unsigned long long* accum;    // [n_local_pixels*3] 32.32 fixed-point colour sums
     unsigned long long* counter;  // work-queue head
     unsigned long long* stats;    // {samples, segments, depth_capped, absorbed, (BVH tests), NaN samples}
-    unsigned long long* timeline; // diagnostics (RTZ_TIMELINE=1), else null: per warp {start, queue ran dry, done} in ns, {lockstep, sphere-parallel} iterations after it ran dry, SM id
+    // The drain pool.  A warp that needs new work after the queue has run dry does not keep sweeping all N spheres
+    // for the few long paths it has left (64 slots for them, and nobody to share them with): it parks its live
+    // paths here and retires; drain_kernel then finishes every parked path, one warp per path, spheres across lanes.
+    float4* pool;                 // [pool_cap][4]: {o, |d|} {d, self} {throughput, bounce} {pixel, sample, local pixel, -}
+    unsigned int* pool_count;     // paths parked (trace kernel) ; pool_count[1] = next path to hand out (drain kernel)
+    unsigned long long* timeline; // diagnostics (RTZ_TIMELINE=1), else null: per warp {start, queue ran dry, done} in ns, SM id
 };
 
 // Scenes of up to kMaxConstSpheres spheres travel as a __grid_constant__ kernel parameter: the
@@ -258,33 +250,6 @@ __device__ __forceinline__ unsigned long long globaltimer_ns() {
     return t;
 }
 
-// One chunk of work (warp-uniform), in queue positions q (local pixel = queue_pixel(q)).
-// across == false: samples [next, end) of position q0.  across == true: sample `sample` of positions q0 + [next, end).
-struct Chunk {
-    uint32_t q0 = 0, next = 0, end = 0, sample = 0;
-    bool across = false;
-};
-__device__ __forceinline__ uint32_t queue_pixel(const TraceParams& P, uint32_t q) {
-    return P.order ? __ldg(P.order + q) : q;
-}
-__device__ __forceinline__ void decode_chunk(const TraceParams& P, unsigned long long cid, uint32_t spp, Chunk& c) {
-    if (cid < P.n_body_chunks) {
-        c.q0 = (uint32_t)(cid / P.chunks_per_pixel);
-        const uint32_t part = (uint32_t)(cid - (unsigned long long)c.q0 * P.chunks_per_pixel);
-        c.next = part * P.chunk;
-        c.end = min(c.next + P.chunk, spp);
-        c.sample = 0u, c.across = false;
-    } else {
-        cid -= P.n_body_chunks;
-        c.sample = (uint32_t)(cid / P.tail_blocks);
-        const uint32_t blk = (uint32_t)(cid - (unsigned long long)c.sample * P.tail_blocks);
-        c.q0 = P.tail_first_pixel + blk * P.tail_width;
-        c.next = 0u;
-        c.end = min(P.tail_width, P.n_local_pixels - c.q0);
-        c.across = true;
-    }
-}
-
 // HittableList.hit for ONE path by the whole warp: lane l tests spheres l, l + 32, ... with the arithmetic of the
 // sweep (sign of the expanded discriminant, then the direct-form root, ascending within the lane), and the
 // closest hit is the warp's minimum over (t, sphere index).  That is the hit of the ascending loop: a sphere is
@@ -294,14 +259,17 @@ __device__ __forceinline__ void decode_chunk(const TraceParams& P, unsigned long
 // spheres with 64 slots for them, 6.5 us per bounce on an empty SM (measured with RTZ_TIMELINE: the last 1 % of
 // the warps used to finish 0.4 ms after the other 99 %).  The discriminants of 8 spheres per lane are evaluated
 // back to back so that their loads overlap (the rows are cold in L1: the sweep reads the constant bank).
+template <bool kUniform = false>  // kUniform: every lane already holds the path (drain_kernel) and wants the result
 __device__ __forceinline__ void coop_hit(const float4* __restrict__ geom, const float* __restrict__ wexp, int n,
                                          float tmin, float tmax, const Path& mine, int src, unsigned lane, float& t_out,
                                          int& best_out) {
-    Path q;
-    q.ox = __shfl_sync(0xFFFFFFFFu, mine.ox, src), q.oy = __shfl_sync(0xFFFFFFFFu, mine.oy, src);
-    q.oz = __shfl_sync(0xFFFFFFFFu, mine.oz, src), q.dx = __shfl_sync(0xFFFFFFFFu, mine.dx, src);
-    q.dy = __shfl_sync(0xFFFFFFFFu, mine.dy, src), q.dz = __shfl_sync(0xFFFFFFFFu, mine.dz, src);
-    q.len = __shfl_sync(0xFFFFFFFFu, mine.len, src), q.self = __shfl_sync(0xFFFFFFFFu, mine.self, src);
+    Path q = mine;
+    if (!kUniform) {
+        q.ox = __shfl_sync(0xFFFFFFFFu, mine.ox, src), q.oy = __shfl_sync(0xFFFFFFFFu, mine.oy, src);
+        q.oz = __shfl_sync(0xFFFFFFFFu, mine.oz, src), q.dx = __shfl_sync(0xFFFFFFFFu, mine.dx, src);
+        q.dy = __shfl_sync(0xFFFFFFFFu, mine.dy, src), q.dz = __shfl_sync(0xFFFFFFFFu, mine.dz, src);
+        q.len = __shfl_sync(0xFFFFFFFFu, mine.len, src), q.self = __shfl_sync(0xFFFFFFFFu, mine.self, src);
+    }
     const float tmin_d = tmin * q.len;
     float closest = tmax * q.len;
     int best = -1;
@@ -331,7 +299,25 @@ __device__ __forceinline__ void coop_hit(const float4* __restrict__ geom, const 
         const int b2 = __shfl_xor_sync(0xFFFFFFFFu, best, o);
         if (t2 < closest || (t2 == closest && (unsigned)b2 < (unsigned)best)) closest = t2, best = b2;  // -1 = none
     }
-    if ((int)lane == src) t_out = closest, best_out = best;
+    if (kUniform || (int)lane == src) t_out = closest, best_out = best;
+}
+
+__device__ __forceinline__ void park_path(float4* __restrict__ e, const Slot& s) {
+    const Path& p = s.path;
+    e[0] = make_float4(p.ox, p.oy, p.oz, p.len);
+    e[1] = make_float4(p.dx, p.dy, p.dz, __int_as_float(p.self));
+    e[2] = make_float4(p.tr, p.tg, p.tb, __uint_as_float(p.bounce));
+    e[3] = make_float4(__uint_as_float(s.key.pixel), __uint_as_float(s.key.sample), __uint_as_float(s.lp), 0.f);
+}
+__device__ __forceinline__ void unpark_path(const float4* __restrict__ e, uint32_t k0, uint32_t k1, Slot& s) {
+    const float4 a = e[0], b = e[1], c = e[2], d = e[3];
+    Path& p = s.path;
+    p.ox = a.x, p.oy = a.y, p.oz = a.z, p.len = a.w;
+    p.dx = b.x, p.dy = b.y, p.dz = b.z, p.self = __float_as_int(b.w);
+    p.tr = c.x, p.tg = c.y, p.tb = c.z, p.bounce = __float_as_uint(c.w);
+    s.key = RngKey{k0, k1, __float_as_uint(d.x), __float_as_uint(d.y)};
+    s.lp = __float_as_uint(d.z);
+    s.alive = true;
 }
 
 // a staged camera ray (trace_body's warp-cooperative regeneration): origin, unit direction, |direction|
@@ -343,15 +329,14 @@ __device__ __forceinline__ void take_camera_ray(const float* stage, uint32_t j, 
     p.self = -1;
     p.bounce = 0;
 }
-constexpr int kStageFloats = 9 * 64;  // per warp: 9 rows (ray, |direction|, pixel id, local pixel) of 64 rays (two slots per lane)
+constexpr int kStageFloats = 7 * 64;  // per warp: 7 rows (origin, unit direction, |direction|) of 64 rays (two slots per lane)
 
 template <bool kConstBank, int kBlock>
 __device__ __forceinline__ void trace_body(const TraceParams& P, const float4* __restrict__ pairs,
                                            const float4* __restrict__ gather, float* __restrict__ stage_mem) {
     float* const stage = stage_mem + (threadIdx.x >> 5) * kStageFloats;
-    uint32_t* const stage_u = reinterpret_cast<uint32_t*>(stage);
     unsigned long long* const tl =
-        P.timeline ? P.timeline + 6ull * ((unsigned long long)blockIdx.x * (kBlock / 32) + (threadIdx.x >> 5)) : nullptr;
+        P.timeline ? P.timeline + 4ull * ((unsigned long long)blockIdx.x * (kBlock / 32) + (threadIdx.x >> 5)) : nullptr;
     if (tl && (threadIdx.x & 31u) == 0u) tl[0] = globaltimer_ns();
     // material rows are touched once per HIT (not per test): they stay in global memory / L1
     const float4* s_aux = P.aux;
@@ -370,9 +355,8 @@ __device__ __forceinline__ void trace_body(const TraceParams& P, const float4* _
 
     // warp-uniform chunk state (parking it in shared memory between regenerations was tried: ptxas then no longer
     // treats the branches on it as uniform and the sweep leaves the uniform datapath)
+    uint32_t ch_lp = 0, ch_x = 0, ch_y = 0, ch_next = 0, ch_end = 0;
     bool exhausted = false;
-    Chunk ch;
-    uint32_t ch_lp = 0, ch_x = 0, ch_y = 0;  // the pixel of a one-pixel chunk
 
     // work counters, per warp, from the votes: a slot that was live and is free now has finished a sample
     unsigned long long n_seg = 0;
@@ -385,7 +369,7 @@ __device__ __forceinline__ void trace_body(const TraceParams& P, const float4* _
         n_samp += __popc(prev_a & need_a) + __popc(prev_b & need_b);
         if (need_a | need_b) {
             while ((need_a | need_b) && !exhausted) {
-                if (ch.next >= ch.end) {
+                if (ch_next >= ch_end) {
                     unsigned long long cid = 0;
                     if (lane == 0) cid = atomicAdd(P.counter, 1ULL);
                     cid = __shfl_sync(0xFFFFFFFFu, cid, 0);
@@ -396,75 +380,67 @@ __device__ __forceinline__ void trace_body(const TraceParams& P, const float4* _
                         if (tl && lane == 0u) tl[1] = globaltimer_ns();
                         break;
                     }
-                    // (decoded into a temporary and committed only behind the `continue`: written the other way
-                    // round ptxas no longer proves the loop converged and the sweep leaves the uniform datapath)
-                    Chunk c;
-                    decode_chunk(P, cid, cam.spp, c);
-                    uint32_t x = 0, y = 0;
-                    const uint32_t lp = c.across ? 0u : queue_pixel(P, c.q0);
-                    const bool padding = !c.across && !local_to_global(P.sh, cam.width, cam.height, lp, x, y);
-                    if (__any_sync(0xFFFFFFFFu, padding)) continue;  // a one-pixel chunk of tile padding
-                    ch = c, ch_lp = lp, ch_x = x, ch_y = y;
+                    // (the chunk is committed only behind the `continue`: written the other way round ptxas no
+                    // longer proves the loop converged and the sweep leaves the uniform datapath)
+                    const uint32_t lp = (uint32_t)(cid / P.chunks_per_pixel);
+                    const uint32_t part = (uint32_t)(cid - (unsigned long long)lp * P.chunks_per_pixel);
+                    uint32_t x, y;
+                    const bool inside = local_to_global(P.sh, cam.width, cam.height, lp, x, y);
+                    if (__any_sync(0xFFFFFFFFu, !inside)) continue;  // tile padding
+                    ch_lp = lp, ch_x = x, ch_y = y;
+                    ch_next = part * P.chunk;
+                    ch_end = min(ch_next + P.chunk, cam.spp);
                 }
-                const bool across = __any_sync(0xFFFFFFFFu, ch.across);
-                const uint32_t avail = ch.end - ch.next;
+                const uint32_t avail = ch_end - ch_next;
                 const uint32_t na = __popc(need_a);
                 const uint32_t rank_a = __popc(need_a & lt_mask);
                 const uint32_t rank_b = na + __popc(need_b & lt_mask);
                 const uint32_t n_gen = min(na + (uint32_t)__popc(need_b), avail);
-                // Camera rays, warp-cooperative: the chunk's next n_gen rays are generated 32 at a time by ALL
+                // Camera rays, warp-cooperative: the chunk's next n_gen samples are generated 32 at a time by ALL
                 // lanes into the warp's staging rows and then picked up by the lanes that own the free slots.
                 // Which lane computes a ray does not matter — its random numbers depend on (pixel, sample) only —
                 // and one full-width pass replaces two passes of ~7 active lanes each (ncu: 28 % of the kernel's
                 // warp-instructions at 16 spheres, profiles/r2_*).
+                const uint32_t pix = ch_y * cam.width + ch_x;
                 for (uint32_t j0 = 0; j0 < n_gen; j0 += 32u) {
                     const uint32_t j = j0 + lane;
                     if (j < n_gen) {
-                        uint32_t x = ch_x, y = ch_y, sample = ch.next + j, lp = ch_lp;
-                        bool inside = true;
-                        if (across) {
-                            lp = queue_pixel(P, ch.q0 + ch.next + j);
-                            inside = local_to_global(P.sh, cam.width, cam.height, lp, x, y);
-                            sample = ch.sample;
-                        }
-                        const uint32_t pix = y * cam.width + x;
-                        stage_u[7 * 64 + j] = inside ? pix : 0xFFFFFFFFu;  // tile padding: no ray
-                        stage_u[8 * 64 + j] = lp;
-                        if (inside) {
-                            const RngKey key{cam.key0, cam.key1, pix, sample};
-                            Path t;
-                            camera_ray(cam, key, x, y, t);
-                            stage[0 * 64 + j] = t.ox, stage[1 * 64 + j] = t.oy, stage[2 * 64 + j] = t.oz;
-                            stage[3 * 64 + j] = t.dx, stage[4 * 64 + j] = t.dy, stage[5 * 64 + j] = t.dz;
-                            stage[6 * 64 + j] = t.len;
-                        }
+                        const RngKey key{cam.key0, cam.key1, pix, ch_next + j};
+                        Path t;
+                        camera_ray(cam, key, ch_x, ch_y, t);
+                        stage[0 * 64 + j] = t.ox, stage[1 * 64 + j] = t.oy, stage[2 * 64 + j] = t.oz;
+                        stage[3 * 64 + j] = t.dx, stage[4 * 64 + j] = t.dy, stage[5 * 64 + j] = t.dz;
+                        stage[6 * 64 + j] = t.len;
                     }
                 }
                 __syncwarp();
                 if (((need_a >> lane) & 1u) && rank_a < n_gen) {
-                    const uint32_t pix = stage_u[7 * 64 + rank_a];
-                    if (pix != 0xFFFFFFFFu) {
-                        A.lp = stage_u[8 * 64 + rank_a];
-                        A.key.pixel = pix, A.key.sample = across ? ch.sample : ch.next + rank_a;
-                        take_camera_ray(stage, rank_a, A.path);
-                        A.alive = true;
-                    }
+                    A.lp = ch_lp;
+                    A.key.pixel = pix, A.key.sample = ch_next + rank_a;
+                    take_camera_ray(stage, rank_a, A.path);
+                    A.alive = true;
                 }
                 if (((need_b >> lane) & 1u) && rank_b < n_gen) {
-                    const uint32_t pix = stage_u[7 * 64 + rank_b];
-                    if (pix != 0xFFFFFFFFu) {
-                        B.lp = stage_u[8 * 64 + rank_b];
-                        B.key.pixel = pix, B.key.sample = across ? ch.sample : ch.next + rank_b;
-                        take_camera_ray(stage, rank_b, B.path);
-                        B.alive = true;
-                    }
+                    B.lp = ch_lp;
+                    B.key.pixel = pix, B.key.sample = ch_next + rank_b;
+                    take_camera_ray(stage, rank_b, B.path);
+                    B.alive = true;
                 }
                 __syncwarp();  // the rows are rewritten by the next round
-                ch.next += n_gen;
+                ch_next += n_gen;
                 need_a = __ballot_sync(0xFFFFFFFFu, !A.alive);
                 need_b = __ballot_sync(0xFFFFFFFFu, !B.alive);
             }
-
+        }
+        if (exhausted && P.pool) {
+            // no more work to hand out: park what is still in flight for drain_kernel and retire
+            const unsigned pa = __ballot_sync(0xFFFFFFFFu, A.alive), pb = __ballot_sync(0xFFFFFFFFu, B.alive);
+            unsigned base = 0u;
+            if (lane == 0u) base = atomicAdd(P.pool_count, (unsigned)(__popc(pa) + __popc(pb)));
+            base = __shfl_sync(0xFFFFFFFFu, base, 0);
+            if (A.alive) park_path(P.pool + 4ull * (base + __popc(pa & lt_mask)), A);
+            if (B.alive) park_path(P.pool + 4ull * (base + __popc(pa) + __popc(pb & lt_mask)), B);
+            break;
         }
         // loop exit on a FRESH warp vote: the condition is warp-uniform by construction, which lets
         // ptxas keep the sweep below on the uniform datapath (uniform loads / UR operands)
@@ -474,17 +450,7 @@ __device__ __forceinline__ void trace_body(const TraceParams& P, const float4* _
         prev_a = live_a, prev_b = live_b;
         float ta = 0.f, tb = 0.f;
         int ia = -1, ib = -1;
-        const bool coop = exhausted && (uint32_t)(__popc(live_a) + __popc(live_b)) <= P.coop_max;
-        if (tl && exhausted && lane == 0u) tl[coop ? 4 : 3] += 1ull;
-        if (coop) {
-            // the tail of the frame: a handful of long paths left in the warp -> one path at a time, spheres across lanes
-            for (unsigned m = live_a; m; m &= m - 1u)
-                coop_hit(P.geom, P.wexp, P.n_spheres, cam.tmin, cam.tmax, A.path, __ffs(m) - 1, lane, ta, ia);
-            for (unsigned m = live_b; m; m &= m - 1u)
-                coop_hit(P.geom, P.wexp, P.n_spheres, cam.tmin, cam.tmax, B.path, __ffs(m) - 1, lane, tb, ib);
-        } else {
-            sweep2<kConstBank>(pairs, gather, P.n_pad, cam.tmin, cam.tmax, A.path, B.path, ta, ia, tb, ib);
-        }
+        sweep2<kConstBank>(pairs, gather, P.n_pad, cam.tmin, cam.tmax, A.path, B.path, ta, ia, tb, ib);
         if (A.alive) finish_or_continue(P, gather, s_aux, s_alb, A, ta, ia);
         if (B.alive) finish_or_continue(P, gather, s_aux, s_alb, B, tb, ib);
         // explicit reconvergence point: with it ptxas proves the loop top converged (no BRA.DIV before
@@ -494,7 +460,7 @@ __device__ __forceinline__ void trace_body(const TraceParams& P, const float4* _
     if (tl && lane == 0u) {
         unsigned smid;
         asm volatile("mov.u32 %0, %smid;" : "=r"(smid));
-        tl[2] = globaltimer_ns(), tl[5] = smid;
+        tl[2] = globaltimer_ns(), tl[3] = smid;
     }
     if (lane == 0u) {  // one atomic per warp and counter
         atomicAdd(P.stats + 0, (unsigned long long)n_samp);
@@ -615,12 +581,12 @@ __device__ __forceinline__ void trace_body_parked(const TraceParams& P, const fl
                     exhausted = true;
                     break;
                 }
-                Chunk c;  // this kernel is launched without a tail region: every chunk is a run of one pixel
-                decode_chunk(P, cid, cam.spp, c);
-                ch_lp = queue_pixel(P, c.q0);
+                ch_lp = (uint32_t)(cid / P.chunks_per_pixel);
+                const uint32_t part = (uint32_t)(cid - (unsigned long long)ch_lp * P.chunks_per_pixel);
                 const bool inside = local_to_global(P.sh, cam.width, cam.height, ch_lp, ch_x, ch_y);
                 if (__any_sync(0xFFFFFFFFu, !inside)) continue;  // tile padding
-                ch_next = c.next, ch_end = c.end;
+                ch_next = part * P.chunk;
+                ch_end = min(ch_next + P.chunk, cam.spp);
             }
             const uint32_t n = min(total, ch_end - ch_next);
             uint32_t before = 0;
@@ -796,31 +762,68 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks) trace_kernel_global(const 
 }
 
 // ---------------------------------------------------------------------------------------------
-// K0: queue order.  One thread per local pixel traces the ray through the pixel centre (no jitter, lens centre)
-// to its first hit; pixels that see a dielectric are queued first, all others behind them.  Scheduling only:
-// the image does not depend on the order (tested), the frame's makespan does — a 256-sample chunk of a pixel
-// inside a glass sphere costs 4x a normal one, and whoever picks such a chunk last finishes last.
+// K1d: the drain.  Finishes the paths the trace kernel parked when its queue ran dry.  The path is warp-uniform:
+// every lane holds the same ray, tests its own spheres (coop_hit), all lanes shade redundantly (one instruction
+// stream either way), lane 0 accumulates.  A bounce costs ~N/32 tests per lane instead of the N a lockstep warp
+// pays for however few paths it has left, so the frame no longer ends with a millisecond of nearly empty warps
+// (RTZ_TIMELINE).  Same arithmetic, same closest hit (minimum over (t, index)): same image.
+// kWarp == false (scenes of fewer spheres than a warp has lanes): one THREAD per path, plain ascending sweep.
 // ---------------------------------------------------------------------------------------------
-__global__ void classify_kernel(const __grid_constant__ TraceParams P, uint32_t* __restrict__ order,
-                                unsigned int* __restrict__ cursors) {
-    const uint32_t lp = blockIdx.x * blockDim.x + threadIdx.x;
-    if (lp >= P.n_local_pixels) return;
-    uint32_t x, y;
-    bool hard = false;
-    if (local_to_global(P.sh, P.cam.width, P.cam.height, lp, x, y)) {
-        const DevCamera& c = P.cam;
-        Path p;
-        p.ox = c.cx, p.oy = c.cy, p.oz = c.cz, p.self = -1, p.bounce = 0, p.tr = p.tg = p.tb = 1.f;
-        const float fx = (float)x, fy = (float)y;
-        set_direction(p, fmaf(c.dvx, fy, fmaf(c.dux, fx, c.p0x)) - c.cx, fmaf(c.dvy, fy, fmaf(c.duy, fx, c.p0y)) - c.cy,
-                      fmaf(c.dvz, fy, fmaf(c.duz, fx, c.p0z)) - c.cz);
-        float t;
-        int best;
-        sweep_rows(P.geom, P.pairs, 0, P.n_spheres, p, c.tmin, c.tmax, t, best);
-        hard = best >= 0 && __float_as_int(__ldg(P.aux + best).w) == kDielectric;
+template <bool kWarp>
+__global__ void __launch_bounds__(128) drain_kernel(const __grid_constant__ TraceParams P) {
+    const unsigned lane = threadIdx.x & 31u;
+    const unsigned n_parked = *P.pool_count;
+    const DevCamera& cam = P.cam;
+    unsigned long long n_seg = 0;
+    unsigned n_samp = 0;
+    for (;;) {
+        unsigned idx = 0u;
+        if (kWarp) {
+            if (lane == 0u) idx = atomicAdd(P.pool_count + 1, 1u);
+            idx = __shfl_sync(0xFFFFFFFFu, idx, 0);
+        } else {
+            idx = atomicAdd(P.pool_count + 1, 1u);
+        }
+        if (idx >= n_parked) break;
+        Slot s;
+        unpark_path(P.pool + 4ull * idx, cam.key0, cam.key1, s);
+        for (;;) {
+            float t = 0.f;
+            int best = -1;
+            if (kWarp)
+                coop_hit<true>(P.geom, P.wexp, P.n_spheres, cam.tmin, cam.tmax, s.path, 0, lane, t, best);
+            else
+                sweep_rows(P.geom, P.pairs, 0, P.n_spheres, s.path, cam.tmin, cam.tmax, t, best);
+            ++n_seg;
+            float sr, sg, sb;
+            int term;
+            if (shade(cam, s.key, P.geom, P.aux, P.albedo, s.path, t, best, sr, sg, sb, term)) {
+                if (!kWarp || lane == 0u) {
+                    const unsigned long long fr = to_fixed(sr), fg = to_fixed(sg), fb = to_fixed(sb);
+                    unsigned long long* px = P.accum + 3ull * s.lp;
+                    if (fr) atomicAdd(px + 0, fr);
+                    if (fg) atomicAdd(px + 1, fg);
+                    if (fb) atomicAdd(px + 2, fb);
+                    if (sr != sr || sg != sg || sb != sb) atomicAdd(P.stats + 5, 1ULL);
+                    if (term == 2) atomicAdd(P.stats + 2, 1ULL);
+                    if (term == 1) atomicAdd(P.stats + 3, 1ULL);
+                }
+                ++n_samp;
+                break;
+            }
+        }
     }
-    const uint32_t pos = hard ? atomicAdd(cursors + 0, 1u) : P.n_local_pixels - 1u - atomicAdd(cursors + 1, 1u);
-    order[pos] = lp;
+    if (!kWarp) {  // per-thread counters -> per warp
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            n_seg += __shfl_xor_sync(0xFFFFFFFFu, n_seg, o);
+            n_samp += __shfl_xor_sync(0xFFFFFFFFu, n_samp, o);
+        }
+    }
+    if (lane == 0u && n_samp) {
+        atomicAdd(P.stats + 0, (unsigned long long)n_samp);
+        atomicAdd(P.stats + 1, n_seg);
+    }
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -127,13 +127,9 @@ def test_image_is_independent_of_the_schedule(pkg, gpu, monkeypatch):
     img0, st0 = gpu.render(cam)
     sh = pkg.rtz_shard(1, 3, 16, 16)
     img0s, st0s = gpu.render(cam, sh)
-    # work-queue shape and the tail's sphere-parallel sweep: chunk sizes, the across-pixel chunks at the end of the
-    # queue (none / every pixel of the frame), the live-path threshold below which a drained warp sweeps one path
-    # with all its lanes (0 = never, 64 = always)
-    for env in ({"RTZ_COOP_MAX": "0"}, {"RTZ_COOP_MAX": "64"}, {"RTZ_CHUNK": "7", "RTZ_TAIL_WIDTH": "1"},
-                {"RTZ_TAIL_WIDTH": "0"}, {"RTZ_TAIL_WIDTH": "64", "RTZ_TAIL_CHUNKS": "100"},
-                {"RTZ_CHUNK": "24", "RTZ_TAIL_WIDTH": "5", "RTZ_TAIL_CHUNKS": "1", "RTZ_COOP_MAX": "40"},
-                {"RTZ_ORDER": "0"}, {"RTZ_ORDER": "0", "RTZ_TAIL_WIDTH": "0", "RTZ_COOP_MAX": "0"}):
+    # work-queue shape and the end of the frame: chunk sizes; live paths parked for the drain kernel when the queue
+    # runs dry, or finished in lockstep by their own warps (RTZ_DRAIN=0, the round-1 schedule)
+    for env in ({"RTZ_CHUNK": "7"}, {"RTZ_CHUNK": "24", "RTZ_DRAIN": "0"}, {"RTZ_DRAIN": "0"}, {"RTZ_CHUNK": "1"}):
         for k, v in env.items():
             monkeypatch.setenv(k, v)
         img, st = gpu.render(cam)

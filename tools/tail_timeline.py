@@ -12,24 +12,19 @@ os.environ["RTZ_TIMELINE"] = "1"; os.environ["RTZ_TIMELINE_OUT"] = out
 def run(shard):
     r.render(cam, shard)
     img, st = r.render(cam, shard)
-    t = np.fromfile(out, dtype=np.uint64).reshape(-1, 6).astype(np.int64)
+    t = np.fromfile(out, dtype=np.uint64).reshape(-1, 4).astype(np.int64)
     t = t[t[:, 2] > 0]
     t0 = t[:, 0].min()
     start, dry, done = (t[:, 0] - t0) / 1e3, (t[:, 1] - t0) / 1e3, (t[:, 2] - t0) / 1e3
     end = done.max()
     dry = np.where(t[:, 1] > 0, dry, done)
     q = lambda a, p: float(np.percentile(a, p))
-    if os.environ.get("DETAIL"):
-        order = np.argsort(done)[-12:]
-        for w in order:
-            print(f"      warp {w:5d} sm {t[w, 5]:3d}: dry {end - dry[w]:7.1f} us, done {end - done[w]:7.1f} us before the end; lockstep iterations after dry {t[w, 3]:4d}, sphere-parallel {t[w, 4]:4d}")
     return (f"trace {st.trace_ms:7.3f} ms | warps {len(t)} | last start +{start.max():6.1f} us | queue dry first {end - dry.min():7.1f} / median {end - q(dry, 50):7.1f} us before the end | "
             f"warps done before the end: 10% {end - q(done, 10):7.1f}  50% {end - q(done, 50):7.1f}  90% {end - q(done, 90):6.1f}  99% {end - q(done, 99):6.1f} us | "
             f"idle warp-time in the tail {np.sum(end - done) / len(t):7.1f} us per warp")
-for name, env in (("round-1 schedule", {"RTZ_TAIL_WIDTH": "0", "RTZ_COOP_MAX": "0", "RTZ_ORDER": "0"}), ("tail across pixels", {"RTZ_COOP_MAX": "0"}),
-                  ("coop drain only", {"RTZ_TAIL_WIDTH": "0"}), ("tail + coop, image order", {"RTZ_ORDER": "0"}), ("glass first + tail + coop", {}), ("both, coop 4", {"RTZ_COOP_MAX": "4"})):
-    for k in ("RTZ_TAIL_WIDTH", "RTZ_TAIL_CHUNKS", "RTZ_COOP_MAX", "RTZ_ORDER"):
+for name, env in (("round-1 schedule (warps finish their own paths)", {"RTZ_DRAIN": "0"}), ("drain kernel (default)", {})):
+    for k in ("RTZ_DRAIN",):
         os.environ.pop(k, None)
     os.environ.update(env)
-    print(f"{name:18s} shard 3/8 : {run(pkg.rtz_shard(3, 8, 4, 4))}", flush=True)
-    print(f"{name:18s} whole     : {run(None)}", flush=True)
+    print(f"{name:48s} shard 3/8 : {run(pkg.rtz_shard(3, 8, 4, 4))}", flush=True)
+    print(f"{name:48s} whole     : {run(None)}", flush=True)
