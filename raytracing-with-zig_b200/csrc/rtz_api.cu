@@ -172,6 +172,7 @@ rtz::DevCamera to_dev_camera(const rtz_camera& c, uint64_t seed) {
     d.width = (uint32_t)c.width, d.height = (uint32_t)c.height;
     d.spp = (uint32_t)c.samples_per_pixel, d.bounce_max = (uint32_t)c.bounce_max;
     d.key0 = (uint32_t)seed, d.key1 = (uint32_t)(seed >> 32);
+    for (uint32_t r = 0; r < 10; ++r) d.rk0[r] = d.key0 + r * 0x9E3779B9u, d.rk1[r] = d.key1 + r * 0xBB67AE85u;
     return d;
 }
 
@@ -180,8 +181,11 @@ rtz::DevCamera to_dev_camera(const rtz_camera& c, uint64_t seed) {
 // after the queue is dry: measured on 1/8 shards of C3, 128 beats 256 (19.79 vs 19.95 ms) and 64 (19.88 ms).  Schedules that cut the END of the queue into small or across-pixel chunks, reorder it (pixels
 // that look into glass first) or let drained warps sweep sphere-parallel were built and measured in round 2
 // (DESIGN.md §5): with the drain kernel none of them is needed, and the reordering even costs 2 %.
-void pick_chunks(rtz::TraceParams& P, uint64_t n_local_pixels) {
-    uint32_t cap = 128u;
+void pick_chunks(const rtz_context* ctx, rtz::TraceParams& P, uint64_t n_local_pixels) {
+    // long frames (>= 128 big chunks per resident warp: C3 whole, C4) take 256, where the per-chunk bookkeeping still
+    // shows (155.1 vs 155.9 ms on C3); short ones (a 1/8 shard of C3: 57 per warp) take 128 for the shorter tail
+    const uint64_t big_chunks_per_warp = n_local_pixels * P.cam.spp / (256ull * (uint64_t)ctx->sm_count * 24);
+    uint32_t cap = big_chunks_per_warp >= 128 ? 256u : 128u;
     if (const char* e = std::getenv("RTZ_CHUNK")) cap = (uint32_t)std::max(1, std::atoi(e));
     P.chunk = P.cam.spp < cap ? P.cam.spp : cap;
     P.chunks_per_pixel = (P.cam.spp + P.chunk - 1) / P.chunk;
@@ -235,7 +239,7 @@ int32_t enqueue_path(rtz_context* ctx, const rtz_camera* cam, const rtz::ShardGe
     P.sh = sg;
     P.geom = ctx->geom.p, P.pairs = ctx->pairs.p, P.aux = ctx->aux.p, P.albedo = ctx->albedo.p, P.wexp = ctx->wexp.p;
     P.n_spheres = ctx->n_spheres, P.n_pad = ctx->n_pad;
-    pick_chunks(P, n_local_pixels);
+    pick_chunks(ctx, P, n_local_pixels);
     P.accum = ctx->accum.p;
     P.counter = ctx->counters.p;
     P.stats = ctx->counters.p + 1;

@@ -49,6 +49,8 @@ struct DevCamera {
     int defocus;             // defocusAngle > 0
     uint32_t width, height, spp, bounce_max;
     uint32_t key0, key1;     // Philox key = seed
+    uint32_t rk0[10], rk1[10];  // its ten round keys (key + r * Weyl constants), precomputed on the host: the kernels
+                                // read them as constant-bank operands of the XORs instead of bumping the key per round
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -63,6 +65,18 @@ __device__ __forceinline__ uint4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_
         const uint32_t n0 = hi1 ^ c1 ^ k0, n2 = hi0 ^ c3 ^ k1;
         c0 = n0, c1 = lo1, c2 = n2, c3 = lo0;
         k0 += 0x9E3779B9u, k1 += 0xBB67AE85u;
+    }
+    return make_uint4(c0, c1, c2, c3);
+}
+
+// the same with the round keys taken from the camera block (kernel parameter = constant bank)
+__device__ __forceinline__ uint4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, const DevCamera& cam) {
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+        const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+        const uint32_t n0 = hi1 ^ c1 ^ cam.rk0[r], n2 = hi0 ^ c3 ^ cam.rk1[r];
+        c0 = n0, c1 = lo1, c2 = n2, c3 = lo0;
     }
     return make_uint4(c0, c1, c2, c3);
 }
@@ -140,7 +154,7 @@ __device__ __forceinline__ void set_direction(Path& p, float dx, float dy, float
 
 // Camera.getRay (src/camera.zig:187-200) for pixel (i,j), sample k.sample.
 __device__ __forceinline__ void camera_ray(const DevCamera& c, const RngKey& k, uint32_t i, uint32_t j, Path& p) {
-    const uint4 r = philox4x32_10(k.pixel, k.sample, 0u, 0u, k.k0, k.k1);
+    const uint4 r = philox4x32_10(k.pixel, k.sample, 0u, 0u, c);
     const float sx = (float)i + (u01(r.x) - 0.5f);  // sampleSquare (:203-209)
     const float sy = (float)j + (u01(r.y) - 0.5f);
     const float psx = fmaf(c.dvx, sy, fmaf(c.dux, sx, c.p0x));
@@ -260,7 +274,7 @@ __device__ __forceinline__ bool shade(const DevCamera& cam, const RngKey& k, con
     if (!front) nx = -nx, ny = -ny, nz = -nz, dn = -dn;
     const int type = __float_as_int(ax.w);
     const uint32_t stream = p.bounce + 1u;  // stream 0 belongs to the camera ray
-    const uint4 r0 = philox4x32_10(k.pixel, k.sample, stream, 0u, k.k0, k.k1);
+    const uint4 r0 = philox4x32_10(k.pixel, k.sample, stream, 0u, cam);
     float ndx, ndy, ndz;
     if (type == kDielectric) {
         // Dielectric.scatter (src/material.zig:82-103)

@@ -259,7 +259,7 @@ __device__ __forceinline__ unsigned long long globaltimer_ns() {
 // spheres with 64 slots for them, 6.5 us per bounce on an empty SM (measured with RTZ_TIMELINE: the last 1 % of
 // the warps used to finish 0.4 ms after the other 99 %).  The discriminants of 8 spheres per lane are evaluated
 // back to back so that their loads overlap (the rows are cold in L1: the sweep reads the constant bank).
-template <bool kUniform = false>  // kUniform: every lane already holds the path (drain_kernel) and wants the result
+template <bool kUniform = false>  // kUniform: every lane already holds the path and wants the result
 __device__ __forceinline__ void coop_hit(const float4* __restrict__ geom, const float* __restrict__ wexp, int n,
                                          float tmin, float tmax, const Path& mine, int src, unsigned lane, float& t_out,
                                          int& best_out) {
@@ -762,65 +762,68 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks) trace_kernel_global(const 
 }
 
 // ---------------------------------------------------------------------------------------------
-// K1d: the drain.  Finishes the paths the trace kernel parked when its queue ran dry.  The path is warp-uniform:
-// every lane holds the same ray, tests its own spheres (coop_hit), all lanes shade redundantly (one instruction
-// stream either way), lane 0 accumulates.  A bounce costs ~N/32 tests per lane instead of the N a lockstep warp
-// pays for however few paths it has left, so the frame no longer ends with a millisecond of nearly empty warps
-// (RTZ_TIMELINE).  Same arithmetic, same closest hit (minimum over (t, index)): same image.
-// kWarp == false (scenes of fewer spheres than a warp has lanes): one THREAD per path, plain ascending sweep.
+// K1d: the drain.  Finishes the paths the trace kernel parked when its queue ran dry.  A warp holds up to 32
+// parked paths, one per lane.  Per bounce the closest hit of every live path is found by the WHOLE warp — the
+// path is broadcast, lane l tests spheres l, l + 32, ... (coop_hit) — and then all lanes shade their own paths
+// together; lanes whose path ended take the next parked one.  A bounce costs ~N/32 tests per lane and live path
+// instead of the N a lockstep warp pays for however few paths it has left, so the frame no longer ends with a
+// millisecond of nearly empty warps (RTZ_TIMELINE).  Same arithmetic, same closest hit (minimum
+// over (t, index)): same image.
+// kWarp == false (scenes of fewer spheres than a warp has lanes): every thread sweeps its own path's spheres.
 // ---------------------------------------------------------------------------------------------
 template <bool kWarp>
 __global__ void __launch_bounds__(128) drain_kernel(const __grid_constant__ TraceParams P) {
     const unsigned lane = threadIdx.x & 31u;
+    const unsigned lt_mask = (1u << lane) - 1u;
     const unsigned n_parked = *P.pool_count;
     const DevCamera& cam = P.cam;
+    Slot s;
+    s.alive = false, s.lp = 0;
+    s.key = RngKey{cam.key0, cam.key1, 0u, 0u};
+    s.path.ox = s.path.oy = s.path.oz = 0.f, s.path.dx = s.path.dy = 0.f, s.path.dz = 1.f;
+    s.path.tr = s.path.tg = s.path.tb = 0.f, s.path.len = 1.f, s.path.self = -1, s.path.bounce = 0;
+    bool empty = false;  // warp-uniform: the pool has nothing left to hand out
     unsigned long long n_seg = 0;
     unsigned n_samp = 0;
     for (;;) {
-        unsigned idx = 0u;
-        if (kWarp) {
-            if (lane == 0u) idx = atomicAdd(P.pool_count + 1, 1u);
-            idx = __shfl_sync(0xFFFFFFFFu, idx, 0);
-        } else {
-            idx = atomicAdd(P.pool_count + 1, 1u);
+        const unsigned need = __ballot_sync(0xFFFFFFFFu, !s.alive);
+        if (need && !empty) {
+            unsigned base = 0u;
+            if (lane == 0u) base = atomicAdd(P.pool_count + 1, (unsigned)__popc(need));
+            base = __shfl_sync(0xFFFFFFFFu, base, 0);
+            const unsigned idx = base + __popc(need & lt_mask);
+            if (((need >> lane) & 1u) && idx < n_parked) unpark_path(P.pool + 4ull * idx, cam.key0, cam.key1, s);
+            empty = base + (unsigned)__popc(need) >= n_parked;
         }
-        if (idx >= n_parked) break;
-        Slot s;
-        unpark_path(P.pool + 4ull * idx, cam.key0, cam.key1, s);
-        for (;;) {
-            float t = 0.f;
-            int best = -1;
-            if (kWarp)
-                coop_hit<true>(P.geom, P.wexp, P.n_spheres, cam.tmin, cam.tmax, s.path, 0, lane, t, best);
-            else
-                sweep_rows(P.geom, P.pairs, 0, P.n_spheres, s.path, cam.tmin, cam.tmax, t, best);
-            ++n_seg;
+        const unsigned live = __ballot_sync(0xFFFFFFFFu, s.alive);
+        if (live == 0u) break;
+        float t = 0.f;
+        int best = -1;
+        if (kWarp) {
+            for (unsigned m = live; m; m &= m - 1u)
+                coop_hit<false>(P.geom, P.wexp, P.n_spheres, cam.tmin, cam.tmax, s.path, __ffs(m) - 1, lane, t, best);
+        } else if (s.alive) {
+            sweep_rows(P.geom, P.pairs, 0, P.n_spheres, s.path, cam.tmin, cam.tmax, t, best);
+        }
+        n_seg += (unsigned)__popc(live);
+        if (s.alive) {
             float sr, sg, sb;
             int term;
             if (shade(cam, s.key, P.geom, P.aux, P.albedo, s.path, t, best, sr, sg, sb, term)) {
-                if (!kWarp || lane == 0u) {
-                    const unsigned long long fr = to_fixed(sr), fg = to_fixed(sg), fb = to_fixed(sb);
-                    unsigned long long* px = P.accum + 3ull * s.lp;
-                    if (fr) atomicAdd(px + 0, fr);
-                    if (fg) atomicAdd(px + 1, fg);
-                    if (fb) atomicAdd(px + 2, fb);
-                    if (sr != sr || sg != sg || sb != sb) atomicAdd(P.stats + 5, 1ULL);
-                    if (term == 2) atomicAdd(P.stats + 2, 1ULL);
-                    if (term == 1) atomicAdd(P.stats + 3, 1ULL);
-                }
-                ++n_samp;
-                break;
+                const unsigned long long fr = to_fixed(sr), fg = to_fixed(sg), fb = to_fixed(sb);
+                unsigned long long* px = P.accum + 3ull * s.lp;
+                if (fr) atomicAdd(px + 0, fr);
+                if (fg) atomicAdd(px + 1, fg);
+                if (fb) atomicAdd(px + 2, fb);
+                if (sr != sr || sg != sg || sb != sb) atomicAdd(P.stats + 5, 1ULL);
+                if (term == 2) atomicAdd(P.stats + 2, 1ULL);
+                if (term == 1) atomicAdd(P.stats + 3, 1ULL);
+                s.alive = false;
             }
         }
+        n_samp += (unsigned)__popc(live & __ballot_sync(0xFFFFFFFFu, !s.alive));
     }
-    if (!kWarp) {  // per-thread counters -> per warp
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            n_seg += __shfl_xor_sync(0xFFFFFFFFu, n_seg, o);
-            n_samp += __shfl_xor_sync(0xFFFFFFFFu, n_samp, o);
-        }
-    }
-    if (lane == 0u && n_samp) {
+    if (lane == 0u && n_seg) {
         atomicAdd(P.stats + 0, (unsigned long long)n_samp);
         atomicAdd(P.stats + 1, n_seg);
     }

@@ -92,4 +92,4 @@ for n in (16, 32, 64, 128, 256, 512, 1024, 2048, 4096):
     img, st = timed(r, cam, reps=2)
     row(f"C5 sweep N={n} 1920x1080 64spp", st, n)
 Path(ROOT / "gpurun_out").mkdir(exist_ok=True)
-(ROOT / "gpurun_out" / "configs_r1.json").write_text(json.dumps(out, indent=1))
+(ROOT / "gpurun_out" / "configs_r2.json").write_text(json.dumps(out, indent=1))
