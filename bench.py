@@ -135,7 +135,7 @@ def run_reference(args, rank: int):
     value = sum(v for v, _, _ in vals) / len(vals)
     ms = 1e3 * sum(d for _, d, _ in vals) / len(vals)
     sample = f"{desc.split(':')[0]} scene+camera at {spp} of {spp_full} spp ({samples / 1e6:.2f} M samples per step)"
-    print(json.dumps({
+    emit({
         "impl": "reference", "metric": "Msamples/s", "value": round(value, 4), "unit": "Msamples/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms, 3),
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
@@ -145,7 +145,7 @@ def run_reference(args, rank: int):
         "e2e": {"value": round(value, 4), "unit": "Msamples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "note": "reference = C++ f64 restatement of the Zig renderer (oracle/, byte-exact on its chapter14.ppm); "
                 "no zig toolchain in the image, so kind=port",
-    }))
+    })
 
 
 # ------------------------------------------------------------------------------------------------
@@ -378,9 +378,30 @@ def run_ours(args, rank: int, world: int, local_rank: int):
                                      "note": "same image through a BVH over the spheres; not the benchmarked path"}
         finally:
             cam.mode = B.MODE_PATH
-    print(json.dumps(line))
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
+
+
+def _quiet_stdout():
+    """Libraries (NCCL's version banner, torchrun's notices) write to stdout; the contract is ONE JSON line there.
+    Everything that is not that line goes to stderr: fd 1 is pointed at fd 2 and the original is kept for `emit`."""
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
+
+
+_REAL_STDOUT = None
+
+
+def emit(line: dict) -> None:
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode()), sys.stdout.flush()
+    else:
+        sys.stdout.flush()
+        os.write(_REAL_STDOUT, data)
 
 
 def main():
@@ -398,6 +419,7 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if args.impl == "reference":
+        _quiet_stdout()
         run_reference(args, rank)
         return
     if world == 1 and args.gpus > 1:
@@ -405,6 +427,7 @@ def main():
         cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
                "--master-addr", "127.0.0.1", "--master-port", "29533", __file__] + sys.argv[1:]
         raise SystemExit(subprocess.call(cmd))
+    _quiet_stdout()
     importlib.import_module("__graft_entry__").build()
     run_ours(args, rank, world, local_rank)
 

@@ -288,6 +288,14 @@ int32_t enqueue_path(rtz_context* ctx, const rtz_camera* cam, const rtz::ShardGe
             rc = launch_trace(ctx, rtz::trace_kernel_const<256, 3>, C, P.n_chunks, 256, 0);
         else if (ctx->variant == 2)
             rc = launch_trace(ctx, rtz::trace_kernel_const<128, 5>, C, P.n_chunks, 128, 0);
+        else if (ctx->variant == 6)  // 28 warps per SM at 72 registers (experiment)
+            rc = launch_trace(ctx, rtz::trace_kernel_const<128, 7>, C, P.n_chunks, 128, 0);
+        else if (ctx->variant == 7)  // 32 warps per SM at 64 registers (experiment)
+            rc = launch_trace(ctx, rtz::trace_kernel_const<128, 8>, C, P.n_chunks, 128, 0);
+        else if (ctx->n_pad <= 64)
+            // shading-bound scenes want warps, not registers: <128,8> (64 registers, 32 warps per SM, 32 B of spills)
+            // measured 4 % faster than <128,6> at 5 and 16 spheres, 1.6 % at 64, 2 % slower at 256 (A/B on one box)
+            rc = launch_trace(ctx, rtz::trace_kernel_const<128, 8>, C, P.n_chunks, 128, 0);
         else
             rc = launch_trace(ctx, rtz::trace_kernel_const<128, 6>, C, P.n_chunks, 128, 0);
     } else if (use_global) {
