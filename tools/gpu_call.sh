@@ -1,4 +1,3 @@
-for i in 1 2; do for v in 0 6 7; do echo "variant $v: $(RTZ_VARIANT=$v python tools/prof_run.py 500 3 1200)"; done; done
-for v in 0 6 7; do echo "variant $v: $(RTZ_VARIANT=$v python tools/ab_small.py | tr '\n' ';')"; done
-RTZ_VARIANT=6 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "mirror" 2>&1 | tail -2
-python bench.py --steps 2 --warmup 3 --no-cpu-baseline 2>/dev/null | wc -l
+N=$(nvidia-smi -L | wc -l)
+python bench.py --gpus $N --steps 10 --warmup 3 > gpurun_out/r2_bench_n${N}_c3.json 2> gpurun_out/r2_bench_n${N}_c3.err; tail -2 gpurun_out/r2_bench_n${N}_c3.err; cat gpurun_out/r2_bench_n${N}_c3.json
+python bench.py --gpus $N --steps 2 --warmup 1 --workload c4 > gpurun_out/r2_bench_n${N}_c4.json 2> gpurun_out/r2_bench_n${N}_c4.err; tail -2 gpurun_out/r2_bench_n${N}_c4.err; cat gpurun_out/r2_bench_n${N}_c4.json
