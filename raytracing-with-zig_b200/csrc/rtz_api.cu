@@ -243,6 +243,19 @@ int32_t enqueue_path(rtz_context* ctx, const rtz_camera* cam, const rtz::ShardGe
     P.accum = ctx->accum.p;
     P.counter = ctx->counters.p;
     P.stats = ctx->counters.p + 1;
+    {
+        // wavefront kernel: a shading or camera-ray pass over r < 32 paths is worth running when it costs less than
+        // sweeping those r paths once more (r/64 of a sweep); measured optimum (same-box A/B, profiles/r2_wave_ab.txt):
+        // 16 of 32 lanes up to 32 spheres, 12 at 64, 8 from 128 on
+        P.wave_shade_min = P.wave_regen_min = ctx->n_pad <= 32 ? 16u : ctx->n_pad <= 64 ? 12u : 8u;
+        auto rcp = [](uint64_t d) -> unsigned long long {  // ceil(2^64 / d); 0 stands for d = 1
+            return d <= 1 ? 0ull : (unsigned long long)(((unsigned __int128)1 << 64) / d) + 1ull;  // d never divides 2^64 unless a power of two: then +1 overshoots by one ulp, still exact for n < 2^32
+        };
+        P.rcp_tile_pixels = rcp(sg.tile_pixels), P.rcp_tiles_x = rcp(sg.tiles_x), P.rcp_tile_w = rcp(sg.tile_w);
+        P.rcp_chunks_per_pixel = rcp(P.chunks_per_pixel);
+        if (const char* e = std::getenv("RTZ_WAVE_SHADE_MIN")) P.wave_shade_min = (uint32_t)std::min(32, std::max(1, std::atoi(e)));
+        if (const char* e = std::getenv("RTZ_WAVE_REGEN_MIN")) P.wave_regen_min = (uint32_t)std::min(32, std::max(1, std::atoi(e)));
+    }
     P.timeline = nullptr;
     if (const char* e = std::getenv("RTZ_TIMELINE")) {  // diagnostics: tools/tail_timeline.py reads the file back
         if (e[0] == '1') {
@@ -282,6 +295,7 @@ int32_t enqueue_path(rtz_context* ctx, const rtz_camera* cam, const rtz::ShardGe
         C.p = P;
         std::memcpy(C.pairs, ctx->h_pairs.data(), (size_t)ctx->n_pad * sizeof(float4));
         // <128,6> (80 registers, 24 warps/SM) is the measured best; the uniform loads want occupancy
+        const bool wave_ok = P.n_chunks <= 0xFFFFFFFFull;  // the wavefront kernel's chunk bookkeeping is 32-bit
         if (ctx->variant == 4)  // experimental: 4 paths per thread, path state parked in shared memory
             rc = launch_trace(ctx, rtz::trace_kernel_const_parked<4, 128, 6>, C, P.n_chunks, 128, 0);
         else if (ctx->variant == 1)
@@ -292,9 +306,17 @@ int32_t enqueue_path(rtz_context* ctx, const rtz_camera* cam, const rtz::ShardGe
             rc = launch_trace(ctx, rtz::trace_kernel_const<128, 7>, C, P.n_chunks, 128, 0);
         else if (ctx->variant == 7)  // 32 warps per SM at 64 registers (experiment)
             rc = launch_trace(ctx, rtz::trace_kernel_const<128, 8>, C, P.n_chunks, 128, 0);
+        else if (ctx->variant == 9 && wave_ok)  // wavefront kernel at 40 / 36 warps per SM (experiments: no faster than 32)
+            rc = launch_trace(ctx, rtz::trace_kernel_wave<128, 10>, C, P.n_chunks, 128, 0);
+        else if (ctx->variant == 10 && wave_ok)
+            rc = launch_trace(ctx, rtz::trace_kernel_wave<128, 9>, C, P.n_chunks, 128, 0);
+        else if (wave_ok && (ctx->variant == 8 || (ctx->variant != 11 && ctx->n_pad <= rtz::kMaxWaveSpheres)))
+            // shading-bound scenes: the warp-level wavefront organisation (compacted shading / camera-ray passes).
+            // Same-box A/B against the lockstep kernel: 1.18x at 16 spheres, 1.14x at 32, 1.08x at 64, 1.03x at 128,
+            // 0.96x at 256 (profiles/r2_wave_ab.txt).  RTZ_VARIANT=11 forces the lockstep kernel, 8 the wavefront.
+            rc = launch_trace(ctx, rtz::trace_kernel_wave<128, 8>, C, P.n_chunks, 128, 0);
         else if (ctx->n_pad <= 64)
-            // shading-bound scenes want warps, not registers: <128,8> (64 registers, 32 warps per SM, 32 B of spills)
-            // measured 4 % faster than <128,6> at 5 and 16 spheres, 1.6 % at 64, 2 % slower at 256 (A/B on one box)
+            // lockstep kernel on a shading-bound scene: warps, not registers (<128,8>: 64 registers, 32 warps per SM)
             rc = launch_trace(ctx, rtz::trace_kernel_const<128, 8>, C, P.n_chunks, 128, 0);
         else
             rc = launch_trace(ctx, rtz::trace_kernel_const<128, 6>, C, P.n_chunks, 128, 0);

@@ -249,6 +249,11 @@ __device__ __forceinline__ void sweep_rows(const float4* __restrict__ geo, const
 //   aux[i]    = {r, 1/r, fuzz | ior, type bits}
 //   albedo[i] = {r, g, b, 1/ior}
 // ---------------------------------------------------------------------------------------------
+// kFlagSelf (the wavefront kernel): a scattered ray that LEAVES the sphere it starts on cannot hit it — with the
+// exact c = 0 its roots are h - |h| and h + |h|, both <= 0 when h = d.(centre - origin) <= 0 — so the sweep may drop
+// that sphere from its candidates.  The flag (bit 30 of `self`) is set from the very h candidate_root would form.
+constexpr int kSelfLeaves = 0x40000000;
+template <bool kFlagSelf = false>
 __device__ __forceinline__ bool shade(const DevCamera& cam, const RngKey& k, const float4* __restrict__ geo,
                                       const float4* __restrict__ aux, const float4* __restrict__ albedo, Path& p,
                                       float t, int best, float& sr, float& sg, float& sb, int& term) {
@@ -326,6 +331,11 @@ __device__ __forceinline__ bool shade(const DevCamera& cam, const RngKey& k, con
     p.ox = px, p.oy = py, p.oz = pz;
     set_direction(p, ndx, ndy, ndz);
     p.self = best;
+    if (kFlagSelf) {
+        const float ocx = gx - px, ocy = gy - py, ocz = gz - pz;
+        const float h = fmaf(p.dz, ocz, fmaf(p.dy, ocy, p.dx * ocx));
+        if (!(h > 0.0f)) p.self = best | kSelfLeaves;
+    }
     return false;
 }
 

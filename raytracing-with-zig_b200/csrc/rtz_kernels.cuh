@@ -42,6 +42,12 @@ struct TraceParams {
     float4* pool;                 // [pool_cap][4]: {o, |d|} {d, self} {throughput, bounce} {pixel, sample, local pixel, -}
     unsigned int* pool_count;     // paths parked (trace kernel) ; pool_count[1] = next path to hand out (drain kernel)
     unsigned long long* timeline; // diagnostics (RTZ_TIMELINE=1), else null: per warp {start, queue ran dry, done} in ns, SM id
+    // trace_kernel_wave only: a shading / regeneration pass over fewer than this many paths is put off to the next
+    // iteration (1 = never put off, 32 = full passes only); the host derives both from the cost of a sweep
+    uint32_t wave_shade_min, wave_regen_min;
+    // ... and the divisors of its chunk bookkeeping as 64-bit reciprocals (ceil(2^64 / d), 0 for d = 1): a chunk of a
+    // 64-spp frame lasts two regeneration passes, and four 32-bit divisions per chunk were 5 % of the kernel
+    unsigned long long rcp_tile_pixels, rcp_tiles_x, rcp_tile_w, rcp_chunks_per_pixel;
 };
 
 // Scenes of up to kMaxConstSpheres spheres travel as a __grid_constant__ kernel parameter: the
@@ -60,6 +66,22 @@ __device__ __forceinline__ bool local_to_global(const ShardGeom& s, uint32_t W, 
     const uint32_t gt = lt * s.world + s.rank;
     const uint32_t ty = gt / s.tiles_x, tx = gt - ty * s.tiles_x;
     const uint32_t wy = within / s.tile_w, wx = within - wy * s.tile_w;
+    x = tx * s.tile_w + wx, y = ty * s.tile_h + wy;
+    return x < W && y < H && ty < s.tiles_y;
+}
+
+// the same with the divisions by launch constants done as multiplications: for n, d < 2^32 and M = ceil(2^64 / d),
+// floor(n / d) = floor(n * M / 2^64) exactly (the excess n * (M - 2^64 / d) / 2^64 is below 2^-32 < 1 / d)
+__device__ __forceinline__ uint32_t div_by(uint32_t n, unsigned long long rcp) {
+    return rcp ? (uint32_t)__umul64hi((unsigned long long)n, rcp) : n;
+}
+__device__ __forceinline__ bool local_to_global_rcp(const ShardGeom& s, unsigned long long rcp_tile_pixels,
+                                                    unsigned long long rcp_tiles_x, unsigned long long rcp_tile_w, uint32_t W,
+                                                    uint32_t H, uint32_t lp, uint32_t& x, uint32_t& y) {
+    const uint32_t lt = div_by(lp, rcp_tile_pixels), within = lp - lt * s.tile_pixels;
+    const uint32_t gt = lt * s.world + s.rank;
+    const uint32_t ty = div_by(gt, rcp_tiles_x), tx = gt - ty * s.tiles_x;
+    const uint32_t wy = div_by(within, rcp_tile_w), wx = within - wy * s.tile_w;
     x = tx * s.tile_w + wx, y = ty * s.tile_h + wy;
     return x < W && y < H && ty < s.tiles_y;
 }
@@ -166,7 +188,7 @@ __device__ __forceinline__ void test_pair(const float4 p0, const float4 p1, cons
 // (Deferring the candidates of several blocks to per-lane lists and resolving them together was built twice and
 // measured on one box: +3.7 % warp-instructions, +0.4 % time.  The 64 paths of a warp come from one pixel, so
 // their candidates coincide and one pass per non-empty block already serves all lanes.)
-template <bool kConstBank>
+template <bool kConstBank, bool kSkipSelf = false>
 __device__ __forceinline__ void sweep2(const float4* __restrict__ pairs, const float4* __restrict__ gather, int n_pad,
                                        float tmin, float tmax, const Path& a, const Path& b, float& ta, int& ia,
                                        float& tb, int& ib) {
@@ -189,7 +211,12 @@ __device__ __forceinline__ void sweep2(const float4* __restrict__ pairs, const f
                 test_pair(p0, p1, b, kb, mb);
             }
         }
-        const unsigned canda = ~ma, candb = ~mb;
+        unsigned canda = ~ma, candb = ~mb;
+        if (kSkipSelf) {  // a ray that leaves its sphere outwards (shade<true> flagged it) cannot hit it: not a candidate
+            const unsigned ra = (unsigned)(a.self & ~kSelfLeaves) - (unsigned)base, rb = (unsigned)(b.self & ~kSelfLeaves) - (unsigned)base;
+            if ((a.self >> 30) == 1 && ra < (unsigned)cnt) canda &= ~(1u << (cnt - 1 - (int)ra));
+            if ((b.self >> 30) == 1 && rb < (unsigned)cnt) candb &= ~(1u << (cnt - 1 - (int)rb));
+        }
         if (canda | candb) {
             // t_min * len is formed HERE, behind an opaque copy, so that it does not occupy two more
             // registers across the whole sweep of the shared-memory kernel (96 registers at 5 CTAs per SM)
@@ -759,6 +786,262 @@ template <int kBlock, int kMinBlocks>
 __global__ void __launch_bounds__(kBlock, kMinBlocks) trace_kernel_global(const __grid_constant__ TraceParams P) {
     __shared__ float stage[(kBlock / 32) * kStageFloats];
     trace_body<false, kBlock>(P, P.pairs, P.geom, stage);
+}
+
+// ---------------------------------------------------------------------------------------------
+// K1w: the warp-level WAVEFRONT organisation of the same work, for shading-bound scenes (few spheres).
+//
+// In the lockstep kernel above a lane shades the two paths it sweeps, so Material.scatter runs once per slot with
+// whichever lanes happen to hold a hit (ncu at 16 spheres: 20.7 of 32 threads active over the kernel, 13 in
+// shading), and a sweep of 16 spheres is only a tenth of the instructions.  Here the 64 paths of a warp live in
+// SHARED memory, one word per (field, path), and every stage picks the paths it applies to from a compacted list,
+// 32 at a time, whichever lane they were swept by:
+//     sweep   lane l sweeps paths l and l + 32 (the packed two-sphere sweep, unchanged)        -> t, best
+//     sky     misses are finished where they were swept (a dozen instructions + the three REDs)
+//     shade   the hits of all 64 paths, compacted: one full-width pass of Material.scatter per 32 hits
+//     regen   the free paths, compacted: one full-width pass of Camera.getRay per 32 new samples
+// A pass that would run with fewer than wave_*_min paths is put off: its paths simply stay as they are for one
+// more iteration (a hit that is swept again yields the same hit; a free path sweeps a stale ray whose result is
+// ignored), which costs 1/64 of a sweep per path instead of a nearly empty pass — the host sets the thresholds
+// from the sweep's length.  Work is counted where a segment is shaded, so nothing is counted twice.
+// The image cannot depend on any of this: a sample's random numbers are a function of (pixel, sample, bounce)
+// and the pixel sums are integers.  tests/test_gpu_parity.py compares this kernel with the mirror bit for bit.
+// ---------------------------------------------------------------------------------------------
+enum WaveField { wOx, wOy, wOz, wDx, wDy, wDz, wLen, wSelf, wTr, wTg, wTb, wBounce, wSample, wPixel, wLp, wT, wBest, kWaveFields };
+constexpr int kMaxWaveSpheres = 128;  // beyond, the sweep dominates and the lockstep kernel's register-resident paths win (measured)
+constexpr int kWaveWords = kWaveFields * 64 + 32;  // per warp: the fields of 64 paths + two 64-byte index lists
+
+// the sky colour of a path that missed everything (src/camera.zig:171-177), added to its pixel
+__device__ __forceinline__ void wave_add_sky(const TraceParams& P, const float* w, const uint32_t* wu, uint32_t s) {
+    const float al = 0.5f * (w[wDy * 64 + s] + 1.0f);
+    const float wh = 1.0f - al;
+    const float sr = w[wTr * 64 + s] * fmaf(al, 0.5f, wh);
+    const float sg = w[wTg * 64 + s] * fmaf(al, 0.7f, wh);
+    const float sb = w[wTb * 64 + s] * fmaf(al, 1.0f, wh);
+    const unsigned long long fr = to_fixed(sr), fg = to_fixed(sg), fb = to_fixed(sb);
+    unsigned long long* px = P.accum + 3ull * wu[wLp * 64 + s];
+    if (fr) atomicAdd(px + 0, fr);
+    if (fg) atomicAdd(px + 1, fg);
+    if (fb) atomicAdd(px + 2, fb);
+    if (sr != sr || sg != sg || sb != sb) atomicAdd(P.stats + 5, 1ULL);  // NaN sample: adds 0, but is counted
+}
+constexpr uint32_t kWaveSky = 0xFFFFFFFFu;    // wBest of a free path whose sky colour has not been added yet
+constexpr uint32_t kWaveEnded = 0xFFFFFFFEu;  // wBest of a free path that owes nothing
+
+template <int kBlock>
+__device__ __forceinline__ void trace_body_wave(const TraceParams& P, const float4* __restrict__ pairs,
+                                                const float4* __restrict__ gather, float* __restrict__ wave_mem) {
+    float* const w = wave_mem + (threadIdx.x >> 5) * kWaveWords;
+    uint32_t* const wu = reinterpret_cast<uint32_t*>(w);
+    uint8_t* const hit_list = reinterpret_cast<uint8_t*>(w + kWaveFields * 64);
+    uint8_t* const free_list = hit_list + 64;
+    const unsigned lane = threadIdx.x & 31u;
+    const unsigned lt_mask = (1u << lane) - 1u;
+    const DevCamera& cam = P.cam;
+    const uint32_t sa = lane, sb = lane + 32u;  // the two paths this lane sweeps
+
+    // what a path without a sample sweeps (its result is ignored)
+    w[wOx * 64 + sa] = w[wOy * 64 + sa] = w[wOz * 64 + sa] = 0.f, w[wDx * 64 + sa] = w[wDy * 64 + sa] = 0.f;
+    w[wDz * 64 + sa] = 1.f, w[wLen * 64 + sa] = 1.f, wu[wSelf * 64 + sa] = 0xFFFFFFFFu;
+    w[wOx * 64 + sb] = w[wOy * 64 + sb] = w[wOz * 64 + sb] = 0.f, w[wDx * 64 + sb] = w[wDy * 64 + sb] = 0.f;
+    w[wDz * 64 + sb] = 1.f, w[wLen * 64 + sb] = 1.f, wu[wSelf * 64 + sb] = 0xFFFFFFFFu;
+    wu[wBest * 64 + sa] = kWaveEnded, wu[wBest * 64 + sb] = kWaveEnded;
+    __syncwarp();
+
+    bool alive_a = false, alive_b = false;
+    uint32_t ch_lp = 0, ch_x = 0, ch_y = 0, ch_next = 0, ch_end = 0;  // warp-uniform chunk state
+    bool exhausted = false;
+    unsigned long long n_seg = 0;
+    uint32_t n_samp = 0, flip = 0;
+
+    for (;;) {
+        // ---- regen: Camera.getRay for the free paths, 32 new samples per pass, whichever lane owns the path ----
+        if (!exhausted) {
+            const unsigned fa = __ballot_sync(0xFFFFFFFFu, !alive_a), fb = __ballot_sync(0xFFFFFFFFu, !alive_b);
+            const uint32_t nfa = __popc(fa), n_free = nfa + __popc(fb);
+            const uint32_t rem = n_free & 31u;
+            const uint32_t n_fill = (n_free - rem) + (rem >= P.wave_regen_min ? rem : 0u);
+            if (n_fill) {
+                const uint32_t rank_a = __popc(fa & lt_mask), rank_b = nfa + __popc(fb & lt_mask);
+                if (!alive_a) free_list[rank_a] = (uint8_t)sa;
+                if (!alive_b) free_list[rank_b] = (uint8_t)sb;
+                __syncwarp();
+                uint32_t done = 0;
+                while (done < n_fill && !exhausted) {
+                    const uint32_t n_batch = min(32u, n_fill - done);
+                    // the batch takes the next n_batch samples of the queue; it may run over the end of a chunk
+                    // into the next pixel, so pixel and sample are per-lane values here
+                    uint32_t filled = 0, my_x = 0, my_y = 0, my_lp = 0, my_sample = 0;
+                    bool have = false;
+                    while (filled < n_batch) {
+                        if (ch_next >= ch_end) {
+                            unsigned long long cid = 0;
+                            if (lane == 0) cid = atomicAdd(P.counter, 1ULL);
+                            cid = __shfl_sync(0xFFFFFFFFu, cid, 0);
+                            if (__any_sync(0xFFFFFFFFu, cid >= P.n_chunks)) {
+                                exhausted = true;
+                                break;
+                            }
+                            // (the host launches this kernel only for frames of fewer than 2^32 chunks)
+                            const uint32_t lp = div_by((uint32_t)cid, P.rcp_chunks_per_pixel);
+                            const uint32_t part = (uint32_t)cid - lp * P.chunks_per_pixel;
+                            uint32_t x, y;
+                            const bool inside = local_to_global_rcp(P.sh, P.rcp_tile_pixels, P.rcp_tiles_x, P.rcp_tile_w,
+                                                                    cam.width, cam.height, lp, x, y);
+                            if (__any_sync(0xFFFFFFFFu, !inside)) continue;  // tile padding
+                            ch_lp = lp, ch_x = x, ch_y = y;
+                            ch_next = part * P.chunk;
+                            ch_end = min(ch_next + P.chunk, cam.spp);
+                        }
+                        const uint32_t take = min(n_batch - filled, ch_end - ch_next);
+                        if (lane - filled < take) {  // filled <= lane < filled + take
+                            my_x = ch_x, my_y = ch_y, my_lp = ch_lp, my_sample = ch_next + (lane - filled);
+                            have = true;
+                        }
+                        filled += take, ch_next += take;
+                    }
+                    if (lane < n_batch) {
+                        // the pass first retires the path that held the slot: a miss still owes its sky colour
+                        const uint32_t s = free_list[done + lane];
+                        if (wu[wBest * 64 + s] == kWaveSky) {
+                            wave_add_sky(P, w, wu, s);
+                            wu[wBest * 64 + s] = kWaveEnded;
+                        }
+                    }
+                    if (have) {
+                        const uint32_t pix = my_y * cam.width + my_x;
+                        const RngKey key{cam.key0, cam.key1, pix, my_sample};
+                        Path t;
+                        camera_ray(cam, key, my_x, my_y, t);
+                        const uint32_t s = free_list[done + lane];
+                        w[wOx * 64 + s] = t.ox, w[wOy * 64 + s] = t.oy, w[wOz * 64 + s] = t.oz;
+                        w[wDx * 64 + s] = t.dx, w[wDy * 64 + s] = t.dy, w[wDz * 64 + s] = t.dz;
+                        w[wLen * 64 + s] = t.len, wu[wSelf * 64 + s] = 0xFFFFFFFFu;
+                        w[wTr * 64 + s] = 1.0f, w[wTg * 64 + s] = 1.0f, w[wTb * 64 + s] = 1.0f;
+                        wu[wBounce * 64 + s] = 0u, wu[wSample * 64 + s] = my_sample, wu[wPixel * 64 + s] = pix;
+                        wu[wLp * 64 + s] = my_lp;
+                    }
+                    done += filled;
+                }
+                __syncwarp();
+                if (!alive_a && rank_a < done) alive_a = true;
+                if (!alive_b && rank_b < done) alive_b = true;
+            }
+        }
+        if (exhausted) {  // no regeneration pass will retire the free paths any more: add what they owe
+            if (!alive_a && wu[wBest * 64 + sa] == kWaveSky) wave_add_sky(P, w, wu, sa), wu[wBest * 64 + sa] = kWaveEnded;
+            if (!alive_b && wu[wBest * 64 + sb] == kWaveSky) wave_add_sky(P, w, wu, sb), wu[wBest * 64 + sb] = kWaveEnded;
+        }
+        if (exhausted && P.pool) {
+            // no more work to hand out: park what is still in flight for drain_kernel and retire (a hit that was
+            // put off is parked as it was before its sweep; the drain sweeps it again)
+            const unsigned pa = __ballot_sync(0xFFFFFFFFu, alive_a), pb = __ballot_sync(0xFFFFFFFFu, alive_b);
+            unsigned base = 0u;
+            if (lane == 0u) base = atomicAdd(P.pool_count, (unsigned)(__popc(pa) + __popc(pb)));
+            base = __shfl_sync(0xFFFFFFFFu, base, 0);
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const uint32_t s = h ? sb : sa;
+                if (h ? alive_b : alive_a) {
+                    float4* e = P.pool + 4ull * (base + (h ? __popc(pa) + __popc(pb & lt_mask) : __popc(pa & lt_mask)));
+                    e[0] = make_float4(w[wOx * 64 + s], w[wOy * 64 + s], w[wOz * 64 + s], w[wLen * 64 + s]);
+                    const int self = (int)wu[wSelf * 64 + s];  // the drain does not know the flag; without it the same hit is found
+                    e[1] = make_float4(w[wDx * 64 + s], w[wDy * 64 + s], w[wDz * 64 + s],
+                                       __int_as_float((self >> 30) == 1 ? self & ~kSelfLeaves : self));
+                    e[2] = make_float4(w[wTr * 64 + s], w[wTg * 64 + s], w[wTb * 64 + s], w[wBounce * 64 + s]);
+                    e[3] = make_float4(w[wPixel * 64 + s], w[wSample * 64 + s], w[wLp * 64 + s], 0.f);
+                }
+            }
+            break;
+        }
+        const unsigned live_a = __ballot_sync(0xFFFFFFFFu, alive_a), live_b = __ballot_sync(0xFFFFFFFFu, alive_b);
+        if ((live_a | live_b) == 0u) break;  // queue drained, every path finished
+
+        // ---- sweep: HittableList.hit for the lane's two paths ----
+        Path a, b;
+        a.ox = w[wOx * 64 + sa], a.oy = w[wOy * 64 + sa], a.oz = w[wOz * 64 + sa];
+        a.dx = w[wDx * 64 + sa], a.dy = w[wDy * 64 + sa], a.dz = w[wDz * 64 + sa];
+        a.len = w[wLen * 64 + sa], a.self = (int)wu[wSelf * 64 + sa];
+        b.ox = w[wOx * 64 + sb], b.oy = w[wOy * 64 + sb], b.oz = w[wOz * 64 + sb];
+        b.dx = w[wDx * 64 + sb], b.dy = w[wDy * 64 + sb], b.dz = w[wDz * 64 + sb];
+        b.len = w[wLen * 64 + sb], b.self = (int)wu[wSelf * 64 + sb];
+        float ta = 0.f, tb = 0.f;
+        int ia = -1, ib = -1;
+        sweep2<true, true>(pairs, gather, P.n_pad, cam.tmin, cam.tmax, a, b, ta, ia, tb, ib);
+        const bool hit_a = alive_a && ia >= 0, hit_b = alive_b && ib >= 0;
+        if (hit_a) w[wT * 64 + sa] = ta, wu[wBest * 64 + sa] = (uint32_t)ia;
+        if (hit_b) w[wT * 64 + sb] = tb, wu[wBest * 64 + sb] = (uint32_t)ib;
+
+        // ---- sky: a miss ends the sample; its colour is added by the pass that reuses the slot ----
+        if (alive_a && ia < 0) wu[wBest * 64 + sa] = kWaveSky, alive_a = false;
+        if (alive_b && ib < 0) wu[wBest * 64 + sb] = kWaveSky, alive_b = false;
+        {
+            const unsigned still_a = __ballot_sync(0xFFFFFFFFu, alive_a), still_b = __ballot_sync(0xFFFFFFFFu, alive_b);
+            const uint32_t n_sky = __popc(live_a & ~still_a) + __popc(live_b & ~still_b);
+            n_seg += n_sky, n_samp += n_sky;
+        }
+
+        // ---- shade: Material.scatter for the hits of all 64 paths, compacted, 32 per pass ----
+        const unsigned ha = __ballot_sync(0xFFFFFFFFu, hit_a), hb = __ballot_sync(0xFFFFFFFFu, hit_b);
+        const uint32_t nha = __popc(ha), n_hit = nha + __popc(hb);
+        const uint32_t hrem = n_hit & 31u;
+        const uint32_t n_proc = (n_hit - hrem) + (hrem >= (exhausted ? 1u : P.wave_shade_min) ? hrem : 0u);
+        if (n_proc) {
+            // the order of the list alternates, so that the hits put off by one iteration lead the next
+            uint32_t rank_a = __popc(ha & lt_mask), rank_b = nha + __popc(hb & lt_mask);
+            if (flip) rank_a = n_hit - 1u - rank_a, rank_b = n_hit - 1u - rank_b;
+            if (hit_a) hit_list[rank_a] = (uint8_t)sa;
+            if (hit_b) hit_list[rank_b] = (uint8_t)sb;
+            __syncwarp();
+            uint32_t n_end = 0;
+            for (uint32_t j0 = 0; j0 < n_proc; j0 += 32u) {
+                const uint32_t j = j0 + lane;
+                bool ended = false;
+                if (j < n_proc) {
+                    const uint32_t s = hit_list[j];
+                    Path p;
+                    p.ox = w[wOx * 64 + s], p.oy = w[wOy * 64 + s], p.oz = w[wOz * 64 + s];
+                    p.dx = w[wDx * 64 + s], p.dy = w[wDy * 64 + s], p.dz = w[wDz * 64 + s];
+                    p.tr = w[wTr * 64 + s], p.tg = w[wTg * 64 + s], p.tb = w[wTb * 64 + s];
+                    p.len = 1.f, p.self = -1, p.bounce = wu[wBounce * 64 + s];
+                    const RngKey key{cam.key0, cam.key1, wu[wPixel * 64 + s], wu[wSample * 64 + s]};
+                    const float t = w[wT * 64 + s];
+                    const int best = (int)wu[wBest * 64 + s];
+                    float sr, sg, sbl;
+                    int term;
+                    if (shade<true>(cam, key, gather, P.aux, P.albedo, p, t, best, sr, sg, sbl, term)) {
+                        // a hit ends a sample black (absorbed by a metal, depth cap): nothing to add
+                        if (term == 2) atomicAdd(P.stats + 2, 1ULL);
+                        if (term == 1) atomicAdd(P.stats + 3, 1ULL);
+                        wu[wBest * 64 + s] = kWaveEnded;  // tells the lane that sweeps this path that it is free
+                        ended = true;
+                    } else {
+                        w[wOx * 64 + s] = p.ox, w[wOy * 64 + s] = p.oy, w[wOz * 64 + s] = p.oz;
+                        w[wDx * 64 + s] = p.dx, w[wDy * 64 + s] = p.dy, w[wDz * 64 + s] = p.dz;
+                        w[wTr * 64 + s] = p.tr, w[wTg * 64 + s] = p.tg, w[wTb * 64 + s] = p.tb;
+                        w[wLen * 64 + s] = p.len, wu[wSelf * 64 + s] = (uint32_t)p.self, wu[wBounce * 64 + s] = p.bounce;
+                    }
+                }
+                n_end += __popc(__ballot_sync(0xFFFFFFFFu, ended));
+            }
+            n_seg += n_proc, n_samp += n_end;
+            __syncwarp();
+            if (hit_a && rank_a < n_proc && wu[wBest * 64 + sa] == kWaveEnded) alive_a = false;
+            if (hit_b && rank_b < n_proc && wu[wBest * 64 + sb] == kWaveEnded) alive_b = false;
+        }
+        flip ^= 1u;
+        __syncwarp();
+    }
+    if (lane == 0u) {  // one atomic per warp and counter
+        atomicAdd(P.stats + 0, (unsigned long long)n_samp);
+        atomicAdd(P.stats + 1, n_seg);
+    }
+}
+
+template <int kBlock, int kMinBlocks>
+__global__ void __launch_bounds__(kBlock, kMinBlocks) trace_kernel_wave(const __grid_constant__ TraceParamsConst C) {
+    __shared__ float wave_mem[(kBlock / 32) * kWaveWords];
+    trace_body_wave<kBlock>(C.p, C.pairs, C.p.geom, wave_mem);
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -139,7 +139,8 @@ def test_image_is_independent_of_the_schedule(pkg, gpu, monkeypatch):
         assert np.array_equal(imgs.cpu().numpy(), img0s.cpu().numpy()), env
         for k in env:
             monkeypatch.delenv(k)
-    for variant in ("1", "2", "4"):
+    # "8": the warp-level wavefront kernel (the default only up to 128 spheres) on this 485-sphere scene
+    for variant in ("1", "2", "4", "8"):
         monkeypatch.setenv("RTZ_VARIANT", variant)
         r = pkg.Renderer(0)
         try:
@@ -152,6 +153,51 @@ def test_image_is_independent_of_the_schedule(pkg, gpu, monkeypatch):
             assert sts.segments == st0s.segments
         finally:
             r.close()
+
+
+@pytest.mark.parametrize("scene", ["chapter13", "sweep16", "sweep128"])
+def test_wavefront_and_lockstep_kernels_agree_on_small_scenes(pkg, gpu, orc, monkeypatch, scene):
+    """Scenes of up to 128 spheres run the warp-level wavefront kernel (paths in shared memory, compacted shading and
+    camera-ray passes, passes over few paths put off); RTZ_VARIANT=11 forces the lockstep kernel.  Same bytes and same
+    work counters, whole and sharded, for every put-off threshold, chunk size and end-of-frame schedule — and both
+    equal the CPU mirror."""
+    if scene == "chapter13":
+        sp, n = R.chapter13_scene()
+        cam = R.build_camera(200, 16.0 / 9.0, spp=37, seed=11, **CH13_CAMERAS["ch13"])
+    else:
+        n = int(scene[5:])
+        prng = orc.orc_prng_new(0xDEADBEEF)
+        sp = (R.Sphere * n)()
+        assert orc.orc_generate_sweep(prng, n, sp) == n
+        cam = R.main_camera(160, 19, seed=5)
+    sh = pkg.rtz_shard(2, 3, 4, 4)
+    gpu.upload(sp, n)
+    img0, st0 = gpu.render(cam)            # default: wavefront
+    img0s, st0s = gpu.render(cam, sh)
+    mrgb, mlin, mst = _mirror(orc, cam, sp, n, cam.seed)
+    assert np.array_equal(img0.cpu().numpy().reshape(-1, 3), mrgb)
+    key0 = (st0.samples, st0.segments, st0.depth_capped, st0.absorbed)
+    assert key0 == (mst.samples, mst.segments, mst.depth_capped, mst.absorbed)
+    envs = [{"RTZ_VARIANT": "11"}, {"RTZ_VARIANT": "11", "RTZ_DRAIN": "0"},
+            {"RTZ_WAVE_SHADE_MIN": "1", "RTZ_WAVE_REGEN_MIN": "1"}, {"RTZ_WAVE_SHADE_MIN": "32", "RTZ_WAVE_REGEN_MIN": "32"},
+            {"RTZ_WAVE_SHADE_MIN": "32", "RTZ_WAVE_REGEN_MIN": "5", "RTZ_CHUNK": "3"}, {"RTZ_DRAIN": "0", "RTZ_CHUNK": "40"},
+            {"RTZ_VARIANT": "9"}, {"RTZ_VARIANT": "10", "RTZ_DRAIN": "0"}]
+    for env in envs:
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        r = pkg.Renderer(0)   # the variant is read when the context is created
+        try:
+            r.upload(sp, n)
+            img, st = r.render(cam)
+            assert np.array_equal(img.cpu().numpy(), img0.cpu().numpy()), env
+            assert (st.samples, st.segments, st.depth_capped, st.absorbed) == key0, env
+            imgs, sts = r.render(cam, sh)
+            assert np.array_equal(imgs.cpu().numpy(), img0s.cpu().numpy()), env
+            assert sts.segments == st0s.segments, env
+        finally:
+            r.close()
+        for k in env:
+            monkeypatch.delenv(k)
 
 
 def test_seed_changes_image_and_is_reported(gpu):

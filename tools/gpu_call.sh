@@ -1,3 +1,2 @@
-N=$(nvidia-smi -L | wc -l)
-python bench.py --gpus $N --steps 10 --warmup 3 > gpurun_out/r2_bench_n${N}_c3.json 2> gpurun_out/r2_bench_n${N}_c3.err; tail -2 gpurun_out/r2_bench_n${N}_c3.err; cat gpurun_out/r2_bench_n${N}_c3.json
-python bench.py --gpus $N --steps 2 --warmup 1 --workload c4 > gpurun_out/r2_bench_n${N}_c4.json 2> gpurun_out/r2_bench_n${N}_c4.err; tail -2 gpurun_out/r2_bench_n${N}_c4.err; cat gpurun_out/r2_bench_n${N}_c4.json
+python -m pytest tests -m gpu -x -q 2>&1 | tail -5
+python tools/wave_ab.py "11,0" "16,32,64,128,256" > gpurun_out/r2_wave_ab4.log 2>&1; cat gpurun_out/r2_wave_ab4.log
