@@ -9,6 +9,7 @@
 #include <algorithm>
 #include <cerrno>
 #include <cmath>
+#include <cstdint>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -829,6 +830,7 @@ int32_t rtz_render(const rtz_camera* cam, const rtz_sphere* sp, uint64_t n, uint
 
 int32_t rtz_write_ppm(const char* path, uint64_t w, uint64_t h, const uint8_t* rgb) {
     if (!path || w > 0xFFFFFFFFull || h > 0xFFFFFFFFull || (!rgb && w * h)) return RTZ_ERR_BAD_ARG;
+    if (w && h > (SIZE_MAX / 3) / w) return RTZ_ERR_BAD_ARG;  // 3 * w * h must fit a size_t
     FILE* f = std::fopen(path, "wb");
     if (!f) {
         g_last_error = std::string(path) + ": " + std::strerror(errno);
