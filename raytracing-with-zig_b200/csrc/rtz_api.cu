@@ -311,11 +311,15 @@ int32_t enqueue_path(rtz_context* ctx, const rtz_camera* cam, const rtz::ShardGe
             rc = launch_trace(ctx, rtz::trace_kernel_wave<128, 10>, C, P.n_chunks, 128, 0);
         else if (ctx->variant == 10 && wave_ok)
             rc = launch_trace(ctx, rtz::trace_kernel_wave<128, 9>, C, P.n_chunks, 128, 0);
-        else if (wave_ok && (ctx->variant == 8 || (ctx->variant != 11 && ctx->n_pad <= rtz::kMaxWaveSpheres)))
-            // shading-bound scenes: the warp-level wavefront organisation (compacted shading / camera-ray passes).
-            // Same-box A/B against the lockstep kernel: 1.18x at 16 spheres, 1.14x at 32, 1.08x at 64, 1.03x at 128,
-            // 0.96x at 256 (profiles/r2_wave_ab.txt).  RTZ_VARIANT=11 forces the lockstep kernel, 8 the wavefront.
+        else if (wave_ok && (ctx->variant == 8 || (ctx->variant == 0 && ctx->n_pad <= 32)))
+            // shading-bound scenes: the warp-level wavefront organisation (compacted shading / camera-ray passes), 64
+            // paths per warp.  Same-box A/B against the lockstep kernel: 1.18x at 16 spheres, 1.14x at 32
+            // (profiles/r2_wave_ab.txt).  RTZ_VARIANT=11 forces the lockstep kernel, 8 / 12 the two wavefront kernels.
             rc = launch_trace(ctx, rtz::trace_kernel_wave<128, 8>, C, P.n_chunks, 128, 0);
+        else if (wave_ok && (ctx->variant == 12 || (ctx->variant == 0 && ctx->n_pad <= rtz::kMaxWaveSpheres)))
+            // ... with 128 paths per warp (four per lane) where the sweep is a third to two thirds of the work: 1.10x at
+            // 64 spheres, 1.06x at 128, 1.015x at 256; 0.99x at 512 and on C3, where the lockstep kernel stays
+            rc = launch_trace(ctx, rtz::trace_kernel_wave_n<4, 128, 6>, C, P.n_chunks, 128, 0);
         else if (ctx->n_pad <= 64)
             // lockstep kernel on a shading-bound scene: warps, not registers (<128,8>: 64 registers, 32 warps per SM)
             rc = launch_trace(ctx, rtz::trace_kernel_const<128, 8>, C, P.n_chunks, 128, 0);

@@ -808,7 +808,7 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks) trace_kernel_global(const 
 // and the pixel sums are integers.  tests/test_gpu_parity.py compares this kernel with the mirror bit for bit.
 // ---------------------------------------------------------------------------------------------
 enum WaveField { wOx, wOy, wOz, wDx, wDy, wDz, wLen, wSelf, wTr, wTg, wTb, wBounce, wSample, wPixel, wLp, wT, wBest, kWaveFields };
-constexpr int kMaxWaveSpheres = 128;  // beyond, the sweep dominates and the lockstep kernel's register-resident paths win (measured)
+constexpr int kMaxWaveSpheres = 256;  // beyond, the sweep dominates and the lockstep kernel's register-resident paths win (measured)
 constexpr int kWaveWords = kWaveFields * 64 + 32;  // per warp: the fields of 64 paths + two 64-byte index lists
 
 // the sky colour of a path that missed everything (src/camera.zig:171-177), added to its pixel
@@ -1042,6 +1042,319 @@ template <int kBlock, int kMinBlocks>
 __global__ void __launch_bounds__(kBlock, kMinBlocks) trace_kernel_wave(const __grid_constant__ TraceParamsConst C) {
     __shared__ float wave_mem[(kBlock / 32) * kWaveWords];
     trace_body_wave<kBlock>(C.p, C.pairs, C.p.geom, wave_mem);
+}
+
+// ---------------------------------------------------------------------------------------------
+// K1w with S paths per lane (S = 4, 128 paths per warp: the default for 33..256 spheres; RTZ_VARIANT=12 forces it).  The same stages as
+// trace_body_wave over 32 * S paths: the ballots, lists and chunk bookkeeping of an iteration and the uniform loads
+// of the sweep are shared by twice as many paths, and a partial pass is a smaller share of the passes.  The sweep keeps
+// only what the packed loop reads (direction + the five constants of the expanded discriminant per path) in
+// registers; origin, |d| and self are re-read from shared memory where a candidate is resolved.
+// ---------------------------------------------------------------------------------------------
+template <int S>
+struct WaveN {
+    static constexpr int kPaths = 32 * S;
+    static constexpr int kWords = kWaveFields * kPaths + 2 * kPaths / 4;  // fields + two byte lists of kPaths entries
+};
+
+template <int S>
+__device__ __forceinline__ void wave_add_sky_n(const TraceParams& P, const float* w, const uint32_t* wu, uint32_t s) {
+    constexpr int N = WaveN<S>::kPaths;
+    const float al = 0.5f * (w[wDy * N + s] + 1.0f);
+    const float wh = 1.0f - al;
+    const float sr = w[wTr * N + s] * fmaf(al, 0.5f, wh);
+    const float sg = w[wTg * N + s] * fmaf(al, 0.7f, wh);
+    const float sb = w[wTb * N + s] * fmaf(al, 1.0f, wh);
+    const unsigned long long fr = to_fixed(sr), fg = to_fixed(sg), fb = to_fixed(sb);
+    unsigned long long* px = P.accum + 3ull * wu[wLp * N + s];
+    if (fr) atomicAdd(px + 0, fr);
+    if (fg) atomicAdd(px + 1, fg);
+    if (fb) atomicAdd(px + 2, fb);
+    if (sr != sr || sg != sg || sb != sb) atomicAdd(P.stats + 5, 1ULL);
+}
+
+template <int S, int kBlock>
+__device__ __forceinline__ void trace_body_wave_n(const TraceParams& P, const float4* __restrict__ pairs,
+                                                  const float4* __restrict__ gather, float* __restrict__ wave_mem) {
+    constexpr int N = WaveN<S>::kPaths;
+    float* const w = wave_mem + (threadIdx.x >> 5) * WaveN<S>::kWords;
+    uint32_t* const wu = reinterpret_cast<uint32_t*>(w);
+    uint8_t* const hit_list = reinterpret_cast<uint8_t*>(w + kWaveFields * N);
+    uint8_t* const free_list = hit_list + N;
+    const unsigned lane = threadIdx.x & 31u;
+    const unsigned lt_mask = (1u << lane) - 1u;
+    const DevCamera& cam = P.cam;
+
+#pragma unroll
+    for (int h = 0; h < S; ++h) {  // what a path without a sample sweeps (its result is ignored)
+        const uint32_t s = lane + 32u * h;
+        w[wOx * N + s] = w[wOy * N + s] = w[wOz * N + s] = 0.f, w[wDx * N + s] = w[wDy * N + s] = 0.f;
+        w[wDz * N + s] = 1.f, w[wLen * N + s] = 1.f, wu[wSelf * N + s] = 0xFFFFFFFFu, wu[wBest * N + s] = kWaveEnded;
+    }
+    __syncwarp();
+
+    unsigned alive = 0u;  // bit h: path lane + 32 h carries a sample
+    uint32_t ch_lp = 0, ch_x = 0, ch_y = 0, ch_next = 0, ch_end = 0;  // warp-uniform chunk state
+    bool exhausted = false;
+    unsigned long long n_seg = 0;
+    uint32_t n_samp = 0, flip = 0;
+
+    for (;;) {
+        // ---- regen ----
+        if (!exhausted) {
+            unsigned fb[S];
+            uint32_t n_free = 0;
+#pragma unroll
+            for (int h = 0; h < S; ++h) fb[h] = __ballot_sync(0xFFFFFFFFu, !((alive >> h) & 1u)), n_free += __popc(fb[h]);
+            const uint32_t rem = n_free & 31u;
+            const uint32_t n_fill = (n_free - rem) + (rem >= P.wave_regen_min ? rem : 0u);
+            if (n_fill) {
+                uint32_t rank[S], before = 0;
+#pragma unroll
+                for (int h = 0; h < S; ++h) {
+                    rank[h] = before + __popc(fb[h] & lt_mask);
+                    before += __popc(fb[h]);
+                    if (!((alive >> h) & 1u)) free_list[rank[h]] = (uint8_t)(lane + 32u * h);
+                }
+                __syncwarp();
+                uint32_t done = 0;
+                while (done < n_fill && !exhausted) {
+                    const uint32_t n_batch = min(32u, n_fill - done);
+                    uint32_t filled = 0, my_x = 0, my_y = 0, my_lp = 0, my_sample = 0;
+                    bool have = false;
+                    while (filled < n_batch) {
+                        if (ch_next >= ch_end) {
+                            unsigned long long cid = 0;
+                            if (lane == 0) cid = atomicAdd(P.counter, 1ULL);
+                            cid = __shfl_sync(0xFFFFFFFFu, cid, 0);
+                            if (__any_sync(0xFFFFFFFFu, cid >= P.n_chunks)) {
+                                exhausted = true;
+                                break;
+                            }
+                            const uint32_t lp = div_by((uint32_t)cid, P.rcp_chunks_per_pixel);
+                            const uint32_t part = (uint32_t)cid - lp * P.chunks_per_pixel;
+                            uint32_t x, y;
+                            const bool inside = local_to_global_rcp(P.sh, P.rcp_tile_pixels, P.rcp_tiles_x, P.rcp_tile_w,
+                                                                    cam.width, cam.height, lp, x, y);
+                            if (__any_sync(0xFFFFFFFFu, !inside)) continue;  // tile padding
+                            ch_lp = lp, ch_x = x, ch_y = y;
+                            ch_next = part * P.chunk;
+                            ch_end = min(ch_next + P.chunk, cam.spp);
+                        }
+                        const uint32_t take = min(n_batch - filled, ch_end - ch_next);
+                        if (lane - filled < take) {
+                            my_x = ch_x, my_y = ch_y, my_lp = ch_lp, my_sample = ch_next + (lane - filled);
+                            have = true;
+                        }
+                        filled += take, ch_next += take;
+                    }
+                    if (lane < n_batch) {
+                        const uint32_t s = free_list[done + lane];
+                        if (wu[wBest * N + s] == kWaveSky) {
+                            wave_add_sky_n<S>(P, w, wu, s);
+                            wu[wBest * N + s] = kWaveEnded;
+                        }
+                    }
+                    if (have) {
+                        const uint32_t pix = my_y * cam.width + my_x;
+                        const RngKey key{cam.key0, cam.key1, pix, my_sample};
+                        Path t;
+                        camera_ray(cam, key, my_x, my_y, t);
+                        const uint32_t s = free_list[done + lane];
+                        w[wOx * N + s] = t.ox, w[wOy * N + s] = t.oy, w[wOz * N + s] = t.oz;
+                        w[wDx * N + s] = t.dx, w[wDy * N + s] = t.dy, w[wDz * N + s] = t.dz;
+                        w[wLen * N + s] = t.len, wu[wSelf * N + s] = 0xFFFFFFFFu;
+                        w[wTr * N + s] = 1.0f, w[wTg * N + s] = 1.0f, w[wTb * N + s] = 1.0f;
+                        wu[wBounce * N + s] = 0u, wu[wSample * N + s] = my_sample, wu[wPixel * N + s] = pix;
+                        wu[wLp * N + s] = my_lp;
+                    }
+                    done += filled;
+                }
+                __syncwarp();
+#pragma unroll
+                for (int h = 0; h < S; ++h)
+                    if (!((alive >> h) & 1u) && rank[h] < done) alive |= 1u << h;
+            }
+        }
+        if (exhausted) {
+#pragma unroll
+            for (int h = 0; h < S; ++h) {
+                const uint32_t s = lane + 32u * h;
+                if (!((alive >> h) & 1u) && wu[wBest * N + s] == kWaveSky) wave_add_sky_n<S>(P, w, wu, s), wu[wBest * N + s] = kWaveEnded;
+            }
+        }
+        if (exhausted && P.pool) {
+            unsigned pb[S];
+            uint32_t total = 0;
+#pragma unroll
+            for (int h = 0; h < S; ++h) pb[h] = __ballot_sync(0xFFFFFFFFu, (alive >> h) & 1u), total += __popc(pb[h]);
+            unsigned base = 0u;
+            if (lane == 0u) base = atomicAdd(P.pool_count, total);
+            base = __shfl_sync(0xFFFFFFFFu, base, 0);
+#pragma unroll
+            for (int h = 0; h < S; ++h) {
+                const uint32_t s = lane + 32u * h;
+                if ((alive >> h) & 1u) {
+                    float4* e = P.pool + 4ull * (base + __popc(pb[h] & lt_mask));
+                    e[0] = make_float4(w[wOx * N + s], w[wOy * N + s], w[wOz * N + s], w[wLen * N + s]);
+                    const int self = (int)wu[wSelf * N + s];
+                    e[1] = make_float4(w[wDx * N + s], w[wDy * N + s], w[wDz * N + s],
+                                       __int_as_float((self >> 30) == 1 ? self & ~kSelfLeaves : self));
+                    e[2] = make_float4(w[wTr * N + s], w[wTg * N + s], w[wTb * N + s], w[wBounce * N + s]);
+                    e[3] = make_float4(w[wPixel * N + s], w[wSample * N + s], w[wLp * N + s], 0.f);
+                }
+                base += __popc(pb[h]);
+            }
+            break;
+        }
+        unsigned live[S], any_live = 0;
+#pragma unroll
+        for (int h = 0; h < S; ++h) live[h] = __ballot_sync(0xFFFFFFFFu, (alive >> h) & 1u), any_live |= live[h];
+        if (any_live == 0u) break;
+
+        // ---- sweep ----
+        float dx[S], dy[S], dz[S], closest[S];
+        RayK k[S];
+        int best[S];
+#pragma unroll
+        for (int h = 0; h < S; ++h) {
+            const uint32_t s = lane + 32u * h;
+            Path q;
+            q.ox = w[wOx * N + s], q.oy = w[wOy * N + s], q.oz = w[wOz * N + s];
+            q.dx = dx[h] = w[wDx * N + s], q.dy = dy[h] = w[wDy * N + s], q.dz = dz[h] = w[wDz * N + s];
+            k[h] = ray_constants(q);
+            asm volatile("" : "+f"(k[h].tx), "+f"(k[h].ty), "+f"(k[h].tz));
+            closest[h] = cam.tmax * w[wLen * N + s];
+            best[h] = -1;
+        }
+        for (int base = 0; base < P.n_pad; base += 32) {
+            const int cnt = min(32, P.n_pad - base);
+            unsigned m[S];
+#pragma unroll
+            for (int h = 0; h < S; ++h) m[h] = 0xFFFFFFFFu;  // 1 = miss
+            const float4* g = pairs + base;
+#pragma unroll 1
+            for (int q0 = 0; q0 < cnt; q0 += 8) {
+#pragma unroll
+                for (int u = 0; u < 8; u += 2) {
+                    const float4 p0 = g[q0 + u], p1 = g[q0 + u + 1];
+#pragma unroll
+                    for (int h = 0; h < S; ++h) {
+                        Path q;
+                        q.dx = dx[h], q.dy = dy[h], q.dz = dz[h];
+                        test_pair(p0, p1, q, k[h], m[h]);
+                    }
+                }
+            }
+            unsigned any = 0;
+#pragma unroll
+            for (int h = 0; h < S; ++h) m[h] = ~m[h], any |= m[h];
+            if (any) {
+#pragma unroll
+                for (int h = 0; h < S; ++h) {
+                    if (m[h]) {
+                        const uint32_t s = lane + 32u * h;
+                        const volatile float* wv = w;  // re-read here, not held in registers across the packed loop
+                        const volatile uint32_t* wuv = wu;
+                        Path q;
+                        q.ox = wv[wOx * N + s], q.oy = wv[wOy * N + s], q.oz = wv[wOz * N + s];
+                        q.dx = dx[h], q.dy = dy[h], q.dz = dz[h];
+                        q.self = (int)wuv[wSelf * N + s];
+                        unsigned c = m[h];
+                        const unsigned rel = (unsigned)(q.self & ~kSelfLeaves) - (unsigned)base;
+                        if ((q.self >> 30) == 1 && rel < (unsigned)cnt) c &= ~(1u << (cnt - 1 - (int)rel));
+                        resolve_candidates(gather, c, base, cnt, q, cam.tmin * wv[wLen * N + s], closest[h], best[h]);
+                    }
+                }
+            }
+        }
+        unsigned hit = 0u;
+#pragma unroll
+        for (int h = 0; h < S; ++h) {
+            const uint32_t s = lane + 32u * h;
+            if ((alive >> h) & 1u) {
+                if (best[h] >= 0) {
+                    w[wT * N + s] = closest[h], wu[wBest * N + s] = (uint32_t)best[h];
+                    hit |= 1u << h;
+                } else {  // sky: the colour is added by the pass that reuses the slot
+                    wu[wBest * N + s] = kWaveSky;
+                    alive &= ~(1u << h);
+                }
+            }
+        }
+        {
+            uint32_t n_sky = 0;
+#pragma unroll
+            for (int h = 0; h < S; ++h) n_sky += __popc(live[h] & ~__ballot_sync(0xFFFFFFFFu, (alive >> h) & 1u));
+            n_seg += n_sky, n_samp += n_sky;
+        }
+
+        // ---- shade ----
+        unsigned hb[S];
+        uint32_t n_hit = 0;
+#pragma unroll
+        for (int h = 0; h < S; ++h) hb[h] = __ballot_sync(0xFFFFFFFFu, (hit >> h) & 1u), n_hit += __popc(hb[h]);
+        const uint32_t hrem = n_hit & 31u;
+        const uint32_t n_proc = (n_hit - hrem) + (hrem >= (exhausted ? 1u : P.wave_shade_min) ? hrem : 0u);
+        if (n_proc) {
+            uint32_t rank[S], before = 0;
+#pragma unroll
+            for (int h = 0; h < S; ++h) {
+                rank[h] = before + __popc(hb[h] & lt_mask);
+                before += __popc(hb[h]);
+                if (flip) rank[h] = n_hit - 1u - rank[h];
+                if ((hit >> h) & 1u) hit_list[rank[h]] = (uint8_t)(lane + 32u * h);
+            }
+            __syncwarp();
+            uint32_t n_end = 0;
+            for (uint32_t j0 = 0; j0 < n_proc; j0 += 32u) {
+                const uint32_t j = j0 + lane;
+                bool ended = false;
+                if (j < n_proc) {
+                    const uint32_t s = hit_list[j];
+                    Path p;
+                    p.ox = w[wOx * N + s], p.oy = w[wOy * N + s], p.oz = w[wOz * N + s];
+                    p.dx = w[wDx * N + s], p.dy = w[wDy * N + s], p.dz = w[wDz * N + s];
+                    p.tr = w[wTr * N + s], p.tg = w[wTg * N + s], p.tb = w[wTb * N + s];
+                    p.len = 1.f, p.self = -1, p.bounce = wu[wBounce * N + s];
+                    const RngKey key{cam.key0, cam.key1, wu[wPixel * N + s], wu[wSample * N + s]};
+                    const float t = w[wT * N + s];
+                    const int bst = (int)wu[wBest * N + s];
+                    float sr, sg, sbl;
+                    int term;
+                    if (shade<true>(cam, key, gather, P.aux, P.albedo, p, t, bst, sr, sg, sbl, term)) {
+                        if (term == 2) atomicAdd(P.stats + 2, 1ULL);
+                        if (term == 1) atomicAdd(P.stats + 3, 1ULL);
+                        wu[wBest * N + s] = kWaveEnded;
+                        ended = true;
+                    } else {
+                        w[wOx * N + s] = p.ox, w[wOy * N + s] = p.oy, w[wOz * N + s] = p.oz;
+                        w[wDx * N + s] = p.dx, w[wDy * N + s] = p.dy, w[wDz * N + s] = p.dz;
+                        w[wTr * N + s] = p.tr, w[wTg * N + s] = p.tg, w[wTb * N + s] = p.tb;
+                        w[wLen * N + s] = p.len, wu[wSelf * N + s] = (uint32_t)p.self, wu[wBounce * N + s] = p.bounce;
+                    }
+                }
+                n_end += __popc(__ballot_sync(0xFFFFFFFFu, ended));
+            }
+            n_seg += n_proc, n_samp += n_end;
+            __syncwarp();
+#pragma unroll
+            for (int h = 0; h < S; ++h)
+                if (((hit >> h) & 1u) && rank[h] < n_proc && wu[wBest * N + lane + 32u * h] == kWaveEnded) alive &= ~(1u << h);
+        }
+        flip ^= 1u;
+        __syncwarp();
+    }
+    if (lane == 0u) {
+        atomicAdd(P.stats + 0, (unsigned long long)n_samp);
+        atomicAdd(P.stats + 1, n_seg);
+    }
+}
+
+template <int S, int kBlock, int kMinBlocks>
+__global__ void __launch_bounds__(kBlock, kMinBlocks) trace_kernel_wave_n(const __grid_constant__ TraceParamsConst C) {
+    __shared__ float wave_mem[(kBlock / 32) * WaveN<S>::kWords];
+    trace_body_wave_n<S, kBlock>(C.p, C.pairs, C.p.geom, wave_mem);
 }
 
 // ---------------------------------------------------------------------------------------------

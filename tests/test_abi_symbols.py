@@ -137,12 +137,13 @@ def test_sweep_stays_on_the_uniform_datapath(pkg):
     sass = "\n".join(body[default[0]])
     assert len(re.findall(r"FFMA2 [^;]*UR\d+\.F32x2", sass)) >= 48, "sweep operands are no longer uniform registers"
     assert "BRA.DIV" not in sass and "LDCU.64" in sass
-    # the same for the wavefront kernel that serves scenes of up to 128 spheres
-    wave = [k for k in body if "trace_kernel_waveILi128ELi8" in k]
-    assert len(wave) == 1, wave
-    sass = "\n".join(body[wave[0]])
-    assert len(re.findall(r"FFMA2 [^;]*UR\d+\.F32x2", sass)) >= 48, "wavefront kernel: sweep operands are no longer uniform registers"
-    assert "BRA.DIV" not in sass and "LDCU.64" in sass
+    # the same for the wavefront kernels that serve scenes of up to 32 / 256 spheres
+    for name in ("trace_kernel_waveILi128ELi8", "trace_kernel_wave_nILi4ELi128ELi6"):
+        wave = [k for k in body if name in k]
+        assert len(wave) == 1, wave
+        sass = "\n".join(body[wave[0]])
+        assert len(re.findall(r"FFMA2 [^;]*UR\d+\.F32x2", sass)) >= 48, name + ": sweep operands are no longer uniform registers"
+        assert "BRA.DIV" not in sass and "LDCU.64" in sass, name
 
 
 def test_no_device_means_error_not_fallback(pkg):

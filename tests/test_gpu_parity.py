@@ -139,8 +139,8 @@ def test_image_is_independent_of_the_schedule(pkg, gpu, monkeypatch):
         assert np.array_equal(imgs.cpu().numpy(), img0s.cpu().numpy()), env
         for k in env:
             monkeypatch.delenv(k)
-    # "8": the warp-level wavefront kernel (the default only up to 128 spheres) on this 485-sphere scene
-    for variant in ("1", "2", "4", "8"):
+    # "8" / "12": the warp-level wavefront kernels (the default only up to 256 spheres) on this 485-sphere scene
+    for variant in ("1", "2", "4", "8", "12"):
         monkeypatch.setenv("RTZ_VARIANT", variant)
         r = pkg.Renderer(0)
         try:
@@ -157,7 +157,7 @@ def test_image_is_independent_of_the_schedule(pkg, gpu, monkeypatch):
 
 @pytest.mark.parametrize("scene", ["chapter13", "sweep16", "sweep128"])
 def test_wavefront_and_lockstep_kernels_agree_on_small_scenes(pkg, gpu, orc, monkeypatch, scene):
-    """Scenes of up to 128 spheres run the warp-level wavefront kernel (paths in shared memory, compacted shading and
+    """Scenes of up to 256 spheres run a warp-level wavefront kernel (paths in shared memory, compacted shading and
     camera-ray passes, passes over few paths put off); RTZ_VARIANT=11 forces the lockstep kernel.  Same bytes and same
     work counters, whole and sharded, for every put-off threshold, chunk size and end-of-frame schedule — and both
     equal the CPU mirror."""
@@ -181,7 +181,10 @@ def test_wavefront_and_lockstep_kernels_agree_on_small_scenes(pkg, gpu, orc, mon
     envs = [{"RTZ_VARIANT": "11"}, {"RTZ_VARIANT": "11", "RTZ_DRAIN": "0"},
             {"RTZ_WAVE_SHADE_MIN": "1", "RTZ_WAVE_REGEN_MIN": "1"}, {"RTZ_WAVE_SHADE_MIN": "32", "RTZ_WAVE_REGEN_MIN": "32"},
             {"RTZ_WAVE_SHADE_MIN": "32", "RTZ_WAVE_REGEN_MIN": "5", "RTZ_CHUNK": "3"}, {"RTZ_DRAIN": "0", "RTZ_CHUNK": "40"},
-            {"RTZ_VARIANT": "9"}, {"RTZ_VARIANT": "10", "RTZ_DRAIN": "0"}]
+            {"RTZ_VARIANT": "9"}, {"RTZ_VARIANT": "10", "RTZ_DRAIN": "0"},
+            # the two wavefront kernels (2 and 4 paths per lane) on every scene, whichever is its default
+            {"RTZ_VARIANT": "8"}, {"RTZ_VARIANT": "12"}, {"RTZ_VARIANT": "12", "RTZ_DRAIN": "0", "RTZ_WAVE_SHADE_MIN": "32"},
+            {"RTZ_VARIANT": "12", "RTZ_CHUNK": "5", "RTZ_WAVE_REGEN_MIN": "1"}]
     for env in envs:
         for k, v in env.items():
             monkeypatch.setenv(k, v)

@@ -1,2 +1,2 @@
-python tools/run_configs.py > gpurun_out/r2c_configs.log 2>&1; tail -3 gpurun_out/r2c_configs.log; ls gpurun_out/*.json | tail -3
-python bench.py --steps 10 --warmup 3 > gpurun_out/r2c_bench_n1.json 2> gpurun_out/r2c_bench_n1.err; cat gpurun_out/r2c_bench_n1.json
+python -m pytest tests -m gpu -x -q 2>&1 | tail -4
+python tools/wave_ab.py "11,0" "16,32,64,128,256" > gpurun_out/r2_wave_ab6.log 2>&1; cat gpurun_out/r2_wave_ab6.log
