@@ -1,4 +1,1 @@
-python -m pytest tests -m gpu -x -q 2>&1 | tail -3
-python bench.py --steps 2 --warmup 1 --no-cpu-baseline > gpurun_out/r2f_bench_plain.json 2>/dev/null && ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/r2_bench_launches_raw.csv python bench.py --steps 2 --warmup 1 --no-cpu-baseline > gpurun_out/r2f_ncu_launch.log 2>&1; tail -1 gpurun_out/r2f_ncu_launch.log | cut -c1-200
-python tools/prof_run.py 500 1 480 > /dev/null && ncu --set full --clock-control none --import-source on -k regex:trace_kernel -c 1 -f -o gpurun_out/r2f_c3_480 python tools/prof_run.py 500 1 480 > gpurun_out/r2f_ncu_c3.log 2>&1; tail -1 gpurun_out/r2f_ncu_c3.log
-python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/r2_bench_reference_arm.json 2>/dev/null; cat gpurun_out/r2_bench_reference_arm.json | cut -c1-300
+python tools/c3_fullsize_parity.py 500 2>&1 | tail -32
